@@ -1,0 +1,152 @@
+/*
+ * samq.h -- C ABI of libsamq.so: the B200 (sm_100a) implementation of the
+ * GPTQ-quantized SAM image-encoder hot path of zhanglei1172/sam-quantization.
+ *
+ * The reference exposes no FFI: its boundary is a Python module-swap API
+ * (gptq_triton/__init__.py:8-12).  Each entry point below replaces one Triton
+ * launch or one chain of eager ATen ops of that path; the reference location it
+ * stands in for is cited per function.  The Python host package
+ * (sam_quantization_b200/) validates shapes/dtypes with the reference's own
+ * exception types and then calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers (device memory unless stated), sizes, and a cudaStream_t
+ *     passed as void*; no torch types.
+ *   - every call is asynchronous on `stream`, allocates nothing, frees nothing
+ *     and keeps no mutable global state except a small cache of TMA descriptors
+ *     (immutable once built) and the thread-local last-error string.
+ *   - return value: SAMQ_OK (0) or a negative samq_status; samq_last_error()
+ *     gives a human-readable reason for the calling thread.
+ *   - fp16 is IEEE binary16 (the reference runs model.half(),
+ *     gptq4sam_infer.py:218); all tensors are dense row-major.
+ */
+#ifndef SAMQ_H_
+#define SAMQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum samq_status {
+  SAMQ_OK = 0,
+  SAMQ_ERR_BAD_SHAPE = -1,       /* reference: AssertionError, quant_linear.py:378-399 */
+  SAMQ_ERR_UNSUPPORTED_BITS = -2, /* reference: NotImplementedError, quant_linear.py:72-73 */
+  SAMQ_ERR_UNSUPPORTED_ARCH = -3, /* reference: RuntimeError, fused_attention.py:314-318 */
+  SAMQ_ERR_LAUNCH = -4,          /* CUDA launch / driver error */
+  SAMQ_ERR_BAD_ARG = -5          /* null pointer, misaligned pointer, bad enum */
+} samq_status;
+
+/* epilogue selector of samq_qlinear_fwd */
+typedef enum samq_epilogue {
+  SAMQ_EPI_NONE = 0, /* y = x.W + bias                         (quant_linear.py:431-435) */
+  SAMQ_EPI_GELU = 1  /* y = gelu_erf(x.W + bias)  lin1 + act   (common.py:25-26)          */
+} samq_epilogue;
+
+/* relw_mode of samq_attn_relpos_fwd: "reference" reproduces the fork's
+ * torch.matmul broadcasting (fused_attention.py:76-78, rel_w indexed by the
+ * query ROW), "upstream" is Meta's einsum("bhwc,wkc->bhwk"). */
+typedef enum samq_relw_mode {
+  SAMQ_RELW_REFERENCE = 0,
+  SAMQ_RELW_UPSTREAM = 1
+} samq_relw_mode;
+
+/* Library / device ---------------------------------------------------------- */
+
+/* ABI version of this header (bumped on any signature change). */
+int samq_abi_version(void);
+
+/* Reason for the last non-OK status returned to the calling thread. */
+const char* samq_last_error(void);
+
+/* SAMQ_OK iff the current CUDA device is compute capability 10.x (B200).
+ * Replaces the capability guard at fused_attention.py:314-318. */
+int samq_device_check(void);
+
+/* Number of kernels this library has launched in this process (all threads);
+ * bench.py reads it around the timed region for "gpu_launches". */
+uint64_t samq_launch_count(void);
+
+/* Packed-weight unpack + dequantise ------------------------------------------
+ * Replaces the in-kernel unpack of matmul4_kernel (quant_linear.py:291-301,
+ * 312-313, 334-339) as a standalone pass:
+ *   q[k,n] = field k%(32/bits) of qweight[k/(32/bits), n]      (2/4/8 bit)
+ *   z[g,n] = field n%(32/bits) of qzeros[g, n/(32/bits)]
+ *   W[k,n] = fp16( fp16(q*s[g,n]) - fp16((z+1)*s[g,n]) ),  g = g_idx[k] or k/groupsize
+ * 3-bit uses the 32-values-in-3-words layout of quant.py:160-180.
+ *   qweight int32 [K*bits/32, N], qzeros int32 [G, N*bits/32], scales fp16 [G, N],
+ *   g_idx int32 [K] or NULL.
+ * transposed == 0: w_out is fp16 [K, N];  transposed != 0: w_out is fp16 [N, K]. */
+int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
+                        const void* scales, const int32_t* g_idx, void* w_out,
+                        int K, int N, int bits, int groupsize, int transposed,
+                        void* stream);
+
+/* Dequant-GEMM ---------------------------------------------------------------
+ * Replaces triton_matmul4 + matmul4_kernel + the separate bias add
+ * (quant_linear.py:231-352, 355-437), with optional fused GELU (common.py:26)
+ * and optional fused residual add (image_encoder.py:204-205):
+ *   y[M,N] = epi( x[M,K] . W[K,N] + bias[N] ) + residual[M,N]
+ * x, y, residual fp16 row-major; bias fp16 [N] or NULL; residual NULL or [M,N]
+ * (may alias y).  fp32 accumulation on tcgen05 tensor cores.
+ * bits == 4 with g_idx == NULL and groupsize % 64 == 0 runs the fused
+ * unpack->TMEM->tcgen05 kernel; every other supported format (bits 2/3/8,
+ * g_idx) needs `workspace` = K*N fp16 (device scratch, may be reused between
+ * calls on the same stream) and runs unpack_dequant + the dense tcgen05 kernel.
+ * Requires K % 64 == 0, N % 128 == 0 (the reference asserts K % 128 == 0 and
+ * N % 256 == 0, quant_linear.py:389-395). */
+int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                     const void* scales, const int32_t* g_idx, const void* bias,
+                     const void* residual, void* y, void* workspace,
+                     int64_t M, int K, int N, int bits, int groupsize,
+                     int epilogue, void* stream);
+
+/* Dense fp16 GEMM on the same tcgen05 kernel: y = epi(x . Wt^T + bias) + residual
+ * with Wt fp16 [N, K] (already dequantised).  Used for the ablation "dequantise
+ * once, then GEMM" and by samq_qlinear_fwd for the non-int4 formats. */
+int samq_dense_linear_fwd(const void* x, const void* wt, const void* bias,
+                          const void* residual, void* y, int64_t M, int K, int N,
+                          int epilogue, void* stream);
+
+/* Attention with decomposed relative-position bias ---------------------------
+ * Replaces the q-slice copy, add_decomposed_rel_pos (2 x get_rel_pos + 2 batched
+ * matmuls) and the Triton flash kernel _fwd_kernel1 of QuantAttention.forward
+ * (fused_attention.py:46-80, 107-133, 159-358):
+ *   qkv  fp16 [B, H*W, 3, heads, hd]   (the qkv QuantLinear output, untouched)
+ *   rel_pos_h fp16 [2H-1, hd], rel_pos_w fp16 [2W-1, hd]
+ *   out  fp16 [B, H*W, heads*hd]
+ *   out = softmax(scale * q k^T + rel_h[m, kh] + rel_w[m, kw]) v
+ * rel_h / rel_w are rounded to fp16 as the reference's torch.matmul does.
+ * Supported: hd in {64, 80}; (H, W) = (64, 64) global or (14, 14) windowed. */
+int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
+                         void* out, int B, int H, int W, int heads, int hd,
+                         float scale, int relw_mode, void* stream);
+
+/* LayerNorm / window partition ------------------------------------------------
+ * y = LayerNorm(x; gamma, beta, eps) over the last dim, fp32 statistics
+ * (nn.LayerNorm(eps=1e-6), image_encoder.py:173,183; build_sam.py:72). */
+int samq_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y,
+                       int64_t rows, int C, float eps, void* stream);
+
+/* LayerNorm fused with window_partition (image_encoder.py:191-195, 282-306;
+ * generic form fq_vit/models/sam/image_encoder.py:481-507):
+ * x fp16 [B, H, W, C] -> y fp16 [B*nH*nW, ws, ws, C], nH = ceil(H/ws); padded
+ * tokens are written as zeros (the pad is applied AFTER the norm). */
+int samq_layernorm_partition_fwd(const void* x, const void* gamma, const void* beta,
+                                 void* y, int B, int H, int W, int C, int ws,
+                                 float eps, void* stream);
+
+/* window_unpartition + crop + residual add (image_encoder.py:201-204, 309-333):
+ * out[b,h,w,:] = shortcut[b,h,w,:] + windows[window(b,h,w), h%ws, w%ws, :].
+ * out may alias shortcut. */
+int samq_unpartition_residual(const void* windows, const void* shortcut, void* out,
+                              int B, int H, int W, int C, int ws, void* stream);
+
+/* out = a + b over n fp16 elements (image_encoder.py:204; global-attention blocks). */
+int samq_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMQ_H_ */

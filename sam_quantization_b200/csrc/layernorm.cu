@@ -1,0 +1,237 @@
+// HBM-bound token-wise kernels of Block.forward (image_encoder.py:189-207):
+// LayerNorm, LayerNorm fused with window_partition (zero padding applied after
+// the norm, image_encoder.py:191-195, 282-306), window_unpartition + crop +
+// residual add (image_encoder.py:201-204, 309-333) and a plain residual add.
+// One warp per token, 16-byte vector accesses, fp32 statistics (two-pass over
+// registers: mean, then sum of squared deviations).
+#include "common.cuh"
+
+namespace samq {
+namespace {
+
+constexpr int kMaxVec = 8;  // 16-byte vectors per lane -> C <= 2048
+
+struct alignas(16) H8 {
+  __half2 v[4];
+};
+
+// normalise one token held by a warp; `src`/`dst` point at the token's C halfs
+__device__ __forceinline__ void warp_layernorm(const __half* __restrict__ src,
+                                               const __half* __restrict__ gamma,
+                                               const __half* __restrict__ beta,
+                                               __half* __restrict__ dst, int C, float eps,
+                                               int lane) {
+  const int nvec = C >> 3;  // 16-byte vectors per token
+  float x[kMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const H8 h = *reinterpret_cast<const H8*>(src + v * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h.v[j]);
+        x[i][2 * j] = f.x;
+        x[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(C);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[i][j] - mean;
+        var += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const H8 g = *reinterpret_cast<const H8*>(gamma + v * 8);
+      const H8 b = *reinterpret_cast<const H8*>(beta + v * 8);
+      H8 o;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 gf = __half22float2(g.v[j]);
+        const float2 bf = __half22float2(b.v[j]);
+        const float y0 = (x[i][2 * j] - mean) * rstd * gf.x + bf.x;
+        const float y1 = (x[i][2 * j + 1] - mean) * rstd * gf.y + bf.y;
+        o.v[j] = __floats2half2_rn(y0, y1);
+      }
+      *reinterpret_cast<H8*>(dst + v * 8) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                 const __half* __restrict__ beta, __half* __restrict__ y, int64_t rows, int C,
+                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  warp_layernorm(x + row * C, gamma, beta, y + row * C, C, eps, lane);
+}
+
+// output token r of [B*nH*nW, ws, ws, C]  <-  input token (b, h, w) or zeros
+__global__ void __launch_bounds__(256)
+layernorm_partition_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                           const __half* __restrict__ beta, __half* __restrict__ y, int B, int H,
+                           int W, int C, int ws, int nH, int nW, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t total = static_cast<int64_t>(B) * nH * nW * ws * ws;
+  if (r >= total) return;
+  const int j = static_cast<int>(r % ws);
+  int64_t q = r / ws;
+  const int i = static_cast<int>(q % ws);
+  q /= ws;
+  const int ww = static_cast<int>(q % nW);
+  q /= nW;
+  const int wh = static_cast<int>(q % nH);
+  const int b = static_cast<int>(q / nH);
+  const int h = wh * ws + i, w = ww * ws + j;
+  __half* dst = y + r * C;
+  if (h < H && w < W) {
+    const __half* src = x + ((static_cast<int64_t>(b) * H + h) * W + w) * C;
+    warp_layernorm(src, gamma, beta, dst, C, eps, lane);
+  } else {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int v = lane; v < (C >> 3); v += 32) *reinterpret_cast<uint4*>(dst + v * 8) = z;
+  }
+}
+
+// one thread per 8 channels of one output token
+__global__ void __launch_bounds__(256)
+unpartition_residual_kernel(const __half* __restrict__ windows, const __half* shortcut,
+                            __half* out, int B, int H, int W, int C, int ws, int nH, int nW) {
+  const int cv = C >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * H * W * cv;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % cv);
+  int64_t tkn = idx / cv;
+  const int w = static_cast<int>(tkn % W);
+  tkn /= W;
+  const int h = static_cast<int>(tkn % H);
+  const int b = static_cast<int>(tkn / H);
+  const int64_t win = (static_cast<int64_t>(b) * nH + h / ws) * nW + w / ws;
+  const int64_t src_tok = (win * ws + h % ws) * ws + w % ws;
+  const H8 a = *reinterpret_cast<const H8*>(windows + src_tok * C + v * 8);
+  const int64_t o = ((static_cast<int64_t>(b) * H + h) * W + w) * C + v * 8;
+  const H8 s = *reinterpret_cast<const H8*>(shortcut + o);
+  H8 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r.v[j] = __hadd2_rn(s.v[j], a.v[j]);
+  *reinterpret_cast<H8*>(out + o) = r;
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const __half* a, const __half* b, __half* out, int64_t nvec) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  const H8 x = *reinterpret_cast<const H8*>(a + i * 8);
+  const H8 y = *reinterpret_cast<const H8*>(b + i * 8);
+  H8 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r.v[j] = __hadd2_rn(x.v[j], y.v[j]);
+  *reinterpret_cast<H8*>(out + i * 8) = r;
+}
+
+int check_ln(const void* x, const void* g, const void* b, const void* y, int C, const char* who) {
+  SAMQ_REQUIRE(x && g && b && y, SAMQ_ERR_BAD_ARG, "%s: null pointer", who);
+  SAMQ_REQUIRE(C > 0 && C % 8 == 0 && C <= kMaxVec * 256, SAMQ_ERR_BAD_SHAPE,
+               "%s: C=%d must be a multiple of 8 and <= %d", who, C, kMaxVec * 256);
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) |
+                reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "%s: pointers must be 16-byte aligned", who);
+  return SAMQ_OK;
+}
+
+}  // namespace
+}  // namespace samq
+
+extern "C" int samq_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y,
+                                  int64_t rows, int C, float eps, void* stream) {
+  using namespace samq;
+  int rc = check_ln(x, gamma, beta, y, C, "samq_layernorm_fwd");
+  if (rc != SAMQ_OK) return rc;
+  SAMQ_REQUIRE(rows >= 0, SAMQ_ERR_BAD_SHAPE, "samq_layernorm_fwd: rows=%lld", (long long)rows);
+  if (rows == 0) return SAMQ_OK;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  layernorm_kernel<<<grid, wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(gamma),
+      reinterpret_cast<const __half*>(beta), reinterpret_cast<__half*>(y), rows, C, eps);
+  count_launch();
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int samq_layernorm_partition_fwd(const void* x, const void* gamma, const void* beta,
+                                            void* y, int B, int H, int W, int C, int ws, float eps,
+                                            void* stream) {
+  using namespace samq;
+  int rc = check_ln(x, gamma, beta, y, C, "samq_layernorm_partition_fwd");
+  if (rc != SAMQ_OK) return rc;
+  SAMQ_REQUIRE(B > 0 && H > 0 && W > 0 && ws > 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_layernorm_partition_fwd: B=%d H=%d W=%d ws=%d", B, H, W, ws);
+  const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
+  const int64_t total = static_cast<int64_t>(B) * nH * nW * ws * ws;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((total + wpb - 1) / wpb);
+  layernorm_partition_kernel<<<grid, wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(gamma),
+      reinterpret_cast<const __half*>(beta), reinterpret_cast<__half*>(y), B, H, W, C, ws, nH, nW,
+      eps);
+  count_launch();
+  return check_launch("layernorm_partition_kernel");
+}
+
+extern "C" int samq_unpartition_residual(const void* windows, const void* shortcut, void* out,
+                                         int B, int H, int W, int C, int ws, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(windows && shortcut && out, SAMQ_ERR_BAD_ARG, "samq_unpartition_residual: null pointer");
+  SAMQ_REQUIRE(B > 0 && H > 0 && W > 0 && ws > 0 && C > 0 && C % 8 == 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_unpartition_residual: B=%d H=%d W=%d C=%d ws=%d", B, H, W, C, ws);
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(windows) | reinterpret_cast<uintptr_t>(shortcut) |
+                reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "samq_unpartition_residual: pointers must be 16-byte aligned");
+  const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
+  const int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  unpartition_residual_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(windows), reinterpret_cast<const __half*>(shortcut),
+      reinterpret_cast<__half*>(out), B, H, W, C, ws, nH, nW);
+  count_launch();
+  return check_launch("unpartition_residual_kernel");
+}
+
+extern "C" int samq_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(a && b && out, SAMQ_ERR_BAD_ARG, "samq_add: null pointer");
+  SAMQ_REQUIRE(n >= 0 && n % 8 == 0, SAMQ_ERR_BAD_SHAPE, "samq_add: n=%lld must be a multiple of 8", (long long)n);
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "samq_add: pointers must be 16-byte aligned");
+  if (n == 0) return SAMQ_OK;
+  const int64_t nvec = n / 8;
+  const unsigned grid = static_cast<unsigned>((nvec + 255) / 256);
+  add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(a), reinterpret_cast<const __half*>(b),
+      reinterpret_cast<__half*>(out), nvec);
+  count_launch();
+  return check_launch("add_kernel");
+}

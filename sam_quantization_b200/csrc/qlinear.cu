@@ -1,0 +1,434 @@
+// Dequant-GEMM for GPTQ QuantLinear on sm_100a:  y = epi(x . W + bias) + residual.
+//
+// Replaces triton_matmul4 / matmul4_kernel (gptq_triton/quant_linear.py:231-437).
+//
+// Orientation.  The kernel computes the TRANSPOSED product D[n, m] = sum_k Wt[n,k] x[m,k]
+// so that the (dequantised) weight is the tcgen05 A operand and can live in TMEM:
+//   A = 128 output features x 64 k   (fused mode: written to TMEM by the dequant
+//                                     warps with tcgen05.st; dense mode: fp16 Wt
+//                                     tile in shared memory, TMA-staged)
+//   B = BM tokens x 64 k             (x tile, K-major, 128-byte swizzle, TMA-staged)
+//   D = 128 lanes (n) x BM fp32 columns (m) in TMEM, two buffers so the epilogue of
+//       tile i overlaps the main loop of tile i+1.
+// Each dequant thread owns ONE output feature n (= its TMEM lane), so scale and
+// zero are thread-constant inside a quantisation group and the packed words
+// qweight[k/8, n] are read coalesced (128 consecutive n per row).
+//
+// Warp roles (384 threads, persistent CTA, one per SM):
+//   warps 0-3   dequant: packed int4 (smem) -> fp16 -> TMEM A stage        [fused]
+//   warps 4-7   epilogue: TMEM D -> +bias -> GELU -> +residual -> fp16 -> global
+//   warp  8     TMA producer: x tiles (+ Wt tiles in dense mode)
+//   warp  9     MMA issuer (one thread): tcgen05.mma kind::f16, commit -> mbarriers
+//   warp 10     TMA producer: packed-weight tiles                           [fused]
+//   warp 11     TMEM allocator
+//
+// Dequant arithmetic is bit-identical to dequant.cu / oracle "stepwise" form:
+//   p = fma(1024+q, s, -1024 s)  == fp16(q*s)  (single rounding of the exact product)
+//   w = p - fp16((z+1)*s)                      (fp16 rounding)
+#include "common.cuh"
+
+namespace samq {
+
+int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                   const int32_t* g_idx, void* w_out, int K, int N, int bits, int groupsize,
+                   int transposed, cudaStream_t st);
+
+namespace {
+
+constexpr int kBN = 128;        // output features per tile (UMMA M)
+constexpr int kBK = 64;         // k per pipeline stage (one 128-byte swizzle row of fp16)
+constexpr int kThreads = 384;
+constexpr int kWStageBytes = 8 * kBN * 4;   // packed int4 tile: 8 words x 128 n
+constexpr int kAStageBytes = kBN * kBK * 2; // dense fp16 Wt tile
+
+template <int BM, bool FUSED>
+struct Cfg {
+  static constexpr int kXStageBytes = BM * kBK * 2;
+  static constexpr int kXStages = FUSED ? 6 : 5;
+  static constexpr int kWStages = 8;                        // fused only
+  static constexpr int kAStages = (512 - 2 * BM) / 32;      // TMEM A stages (fused only)
+  static constexpr int kTmemABase = 2 * BM;                 // column offset of A stages
+  static constexpr int kSmemData =
+      kXStages * kXStageBytes + (FUSED ? kWStages * kWStageBytes : kXStages * kAStageBytes);
+  static constexpr int kNumBars = 2 * kXStages + 2 * kWStages + 2 * 8 + 4;
+  static constexpr int kSmemBytes = kSmemData + kNumBars * 8 + 16 + 1024;  // + alignment slack
+  static_assert(kAStages >= 2 || !FUSED, "need at least two TMEM A stages");
+  static_assert(BM % 32 == 0 && BM <= 256, "BM");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// (a & 0x000f000f) | 0x64006400  ->  two fp16 values 1024 + nibble
+__device__ __forceinline__ uint32_t nib_to_h2(uint32_t w) {
+  return lop3_and_or(w, 0x000f000fu, 0x64006400u);
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_dup(__half h) {
+  const uint32_t u = __half_as_ushort(h);
+  return u | (u << 16);
+}
+
+template <int BM, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 1)
+qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+               const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
+               const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N,
+               int K, int groupsize, int epilogue) {
+  using C = Cfg<BM, FUSED>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sx = smem;
+  uint8_t* sw = sx + C::kXStages * C::kXStageBytes;  // fused: packed W ring; dense: Wt ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemData);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + C::kXStages;
+  uint64_t* w_full = x_empty + C::kXStages;
+  uint64_t* w_empty = w_full + C::kWStages;
+  uint64_t* a_full = w_empty + C::kWStages;
+  uint64_t* a_empty = a_full + 8;
+  uint64_t* acc_full = a_empty + 8;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_kb = K / kBK;
+  const int NT = N / kBN;
+  const int MT = (M + BM - 1) / BM;
+  const int num_tiles = NT * MT;
+
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < C::kXStages; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < C::kWStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 4);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 4);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 11) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer: x (and dense Wt) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % NT, m_tile = t / NT;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&x_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&x_full[s], C::kXStageBytes + (FUSED ? 0 : kAStageBytes));
+          tma_load_2d(sx + s * C::kXStageBytes, &map_x, &x_full[s], kb * kBK, m_tile * BM);
+          if (!FUSED)
+            tma_load_2d(sw + s * kAStageBytes, &map_w, &x_full[s], kb * kBK, n_tile * kBN);
+          if (++s == C::kXStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== TMA producer: packed weights =====================
+    if (FUSED && lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % NT;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], kWStageBytes);
+          tma_load_2d(sw + s * kWStageBytes, &map_w, &w_full[s], n_tile * kBN, kb * 8);
+          if (++s == C::kWStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBN, BM, 0);
+      int xs = 0, as = 0;
+      uint32_t xph = 0, aph = 0;
+      int lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        const int ab = lt & 1;
+        const uint32_t acc_ph = (lt >> 1) & 1;
+        mbar_wait(&acc_empty[ab], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (FUSED) mbar_wait(&a_full[as], aph);
+          mbar_wait(&x_full[xs], xph);
+          tc_fence_after();
+          const uint64_t b_desc =
+              make_smem_desc(smem_u32(sx + xs * C::kXStageBytes), 0, 1024, kLayoutSw128);
+          if (FUSED) {
+            const uint32_t a_tmem = tmem_base + C::kTmemABase + as * 32;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma_ts(d_tmem, a_tmem + k * 8, b_desc + (k * 32 >> 4), idesc, (kb | k) != 0);
+          } else {
+            const uint64_t a_desc =
+                make_smem_desc(smem_u32(sw + xs * kAStageBytes), 0, 1024, kLayoutSw128);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma_ss(d_tmem, a_desc + (k * 32 >> 4), b_desc + (k * 32 >> 4), idesc,
+                        (kb | k) != 0);
+          }
+          tc_commit(&x_empty[xs]);
+          if (FUSED) {
+            tc_commit(&a_empty[as]);
+            if (++as == C::kAStages) { as = 0; aph ^= 1; }
+          }
+          if (++xs == C::kXStages) { xs = 0; xph ^= 1; }
+        }
+        tc_commit(&acc_full[ab]);
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== dequant warps (fused mode) =====================
+    if (FUSED) {
+      const int tid = threadIdx.x;  // 0..127 == TMEM lane == n within tile
+      int ws = 0, as = 0;
+      uint32_t wph = 0, aph = 0;
+      const int kb_per_group = groupsize / kBK;
+      const int zwords = N / 8;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % NT;
+        const int n = n_tile * kBN + tid;
+        const int zshift = (n & 7) * 4;
+        // group constants, prefetched one group ahead
+        __half s_next = scales[n];
+        uint32_t z_next = (static_cast<uint32_t>(qzeros[n >> 3]) >> zshift) & 0xF;
+        uint32_t s2 = 0, c2 = 0, nzs2 = 0;
+        int kb_in_group = 0, g = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (kb_in_group == 0) {
+            const __half s = s_next;
+            const __half zs = __hmul_rn(__uint2half_rn(z_next + 1u), s);
+            s2 = h2_dup(s);
+            c2 = h2_dup(__hneg(__hmul_rn(s, __float2half(1024.f))));
+            nzs2 = h2_dup(__hneg(zs));
+            ++g;
+            if (g * groupsize < K) {
+              s_next = scales[static_cast<int64_t>(g) * N + n];
+              z_next = (static_cast<uint32_t>(qzeros[static_cast<int64_t>(g) * zwords + (n >> 3)]) >> zshift) & 0xF;
+            }
+          }
+          if (++kb_in_group == kb_per_group) kb_in_group = 0;
+
+          mbar_wait(&w_full[ws], wph);
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(sw + ws * kWStageBytes) + tid;
+          uint32_t q[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) q[r] = wp[r * kBN];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&w_empty[ws]);
+          if (++ws == C::kWStages) { ws = 0; wph ^= 1; }
+
+          uint32_t out[32];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const uint32_t w = q[r];
+            // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q
+            uint32_t a = nib_to_h2(w), b = nib_to_h2(w >> 4), c = nib_to_h2(w >> 8),
+                     d = nib_to_h2(w >> 12);
+            a = h2_add(h2_fma(a, s2, c2), nzs2);
+            b = h2_add(h2_fma(b, s2, c2), nzs2);
+            c = h2_add(h2_fma(c, s2, c2), nzs2);
+            d = h2_add(h2_fma(d, s2, c2), nzs2);
+            out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
+            out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
+            out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)
+            out[4 * r + 3] = prmt(c, d, 0x7632);  // (k6,k7)
+          }
+          mbar_wait(&a_empty[as], aph ^ 1);
+          tc_fence_after();
+          tmem_st_x32(tmem_base + C::kTmemABase + as * 32 + (static_cast<uint32_t>(warp * 32) << 16), out);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[as]);
+          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue warps =====================
+    const int e = warp - 4;
+    int lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const int n_tile = t % NT, m_tile = t / NT;
+      const int n = n_tile * kBN + e * 32 + lane;
+      const int ab = lt & 1;
+      const uint32_t acc_ph = (lt >> 1) & 1;
+      const float bv = bias ? __half2float(bias[n]) : 0.f;
+      mbar_wait(&acc_full[ab], acc_ph);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * BM + (static_cast<uint32_t>(e * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BM / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(d_tmem + c * 32, r);
+        tmem_ld_wait();
+        if (c == BM / 32 - 1) {
+          // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+        const int m0 = m_tile * BM + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = m0 + j;
+          if (m < M) {
+            float v = __uint_as_float(r[j]) + bv;
+            if (epilogue == SAMQ_EPI_GELU) v = gelu_erf(v);
+            const size_t off = static_cast<size_t>(m) * N + n;
+            if (residual) v += __half2float(residual[off]);
+            y[off] = __float2half_rn(v);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 11) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BM, bool FUSED>
+int launch_qlinear(const void* x, const void* w, const __half* scales, const int32_t* qzeros,
+                   const __half* bias, const __half* residual, __half* y, int64_t M, int K, int N,
+                   int groupsize, int epilogue, cudaStream_t st) {
+  using C = Cfg<BM, FUSED>;
+  const CUtensorMap* mx = get_tensor_map_2d(x, static_cast<uint64_t>(M), K, static_cast<uint64_t>(K) * 2, BM, kBK, 2, 3);
+  if (!mx) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap* mw =
+      FUSED ? get_tensor_map_2d(w, K / 8, N, static_cast<uint64_t>(N) * 4, 8, kBN, 4, 0)
+            : get_tensor_map_2d(w, N, K, static_cast<uint64_t>(K) * 2, kBN, kBK, 2, 3);
+  if (!mw) return SAMQ_ERR_LAUNCH;
+  auto kern = qlinear_kernel<BM, FUSED>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
+      return SAMQ_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  const int NT = N / kBN;
+  const int64_t MT = (M + BM - 1) / BM;
+  const int64_t tiles = NT * MT;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  kern<<<grid, kThreads, C::kSmemBytes, st>>>(*mx, *mw, scales, qzeros, bias, residual, y,
+                                              static_cast<int>(M), N, K, groupsize, epilogue);
+  count_launch();
+  return check_launch("qlinear_kernel");
+}
+
+int check_common(const void* x, const void* y, int64_t M, int K, int N, int epilogue,
+                 const char* who) {
+  SAMQ_REQUIRE(x && y, SAMQ_ERR_BAD_ARG, "%s: null pointer", who);
+  SAMQ_REQUIRE(M > 0 && M < (1ll << 31) / 2, SAMQ_ERR_BAD_SHAPE, "%s: M=%lld out of range", who, (long long)M);
+  SAMQ_REQUIRE(K > 0 && K % kBK == 0, SAMQ_ERR_BAD_SHAPE, "%s: K=%d must be a positive multiple of %d", who, K, kBK);
+  SAMQ_REQUIRE(N > 0 && N % kBN == 0, SAMQ_ERR_BAD_SHAPE, "%s: N=%d must be a positive multiple of %d", who, N, kBN);
+  SAMQ_REQUIRE(epilogue == SAMQ_EPI_NONE || epilogue == SAMQ_EPI_GELU, SAMQ_ERR_BAD_ARG, "%s: bad epilogue %d", who, epilogue);
+  SAMQ_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0, SAMQ_ERR_BAD_ARG, "%s: x must be 16-byte aligned", who);
+  return SAMQ_OK;
+}
+
+}  // namespace
+
+}  // namespace samq
+
+extern "C" int samq_dense_linear_fwd(const void* x, const void* wt, const void* bias,
+                                     const void* residual, void* y, int64_t M, int K, int N,
+                                     int epilogue, void* stream) {
+  using namespace samq;
+  int rc = check_common(x, y, M, K, N, epilogue, "samq_dense_linear_fwd");
+  if (rc != SAMQ_OK) return rc;
+  SAMQ_REQUIRE(wt && reinterpret_cast<uintptr_t>(wt) % 16 == 0, SAMQ_ERR_BAD_ARG,
+               "samq_dense_linear_fwd: wt must be non-null and 16-byte aligned");
+  return launch_qlinear<192, false>(x, wt, nullptr, nullptr, reinterpret_cast<const __half*>(bias),
+                                    reinterpret_cast<const __half*>(residual),
+                                    reinterpret_cast<__half*>(y), M, K, N, K, epilogue,
+                                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                                const void* scales, const int32_t* g_idx, const void* bias,
+                                const void* residual, void* y, void* workspace, int64_t M, int K,
+                                int N, int bits, int groupsize, int epilogue, void* stream) {
+  using namespace samq;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMQ_REQUIRE(bits == 2 || bits == 3 || bits == 4 || bits == 8, SAMQ_ERR_UNSUPPORTED_BITS,
+               "samq_qlinear_fwd: bits must be 2, 3, 4 or 8 (got %d)", bits);
+  int rc = check_common(x, y, M, K, N, epilogue, "samq_qlinear_fwd");
+  if (rc != SAMQ_OK) return rc;
+  SAMQ_REQUIRE(qweight && qzeros && scales, SAMQ_ERR_BAD_ARG, "samq_qlinear_fwd: null weight pointer");
+  if (groupsize == -1) groupsize = K;
+  SAMQ_REQUIRE(groupsize > 0 && K % groupsize == 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_qlinear_fwd: groupsize=%d must divide K=%d", groupsize, K);
+  const bool fused = bits == 4 && g_idx == nullptr && groupsize % kBK == 0 &&
+                     reinterpret_cast<uintptr_t>(qweight) % 16 == 0;
+  if (fused) {
+    return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
+                                     reinterpret_cast<const __half*>(bias),
+                                     reinterpret_cast<const __half*>(residual),
+                                     reinterpret_cast<__half*>(y), M, K, N, groupsize, epilogue, st);
+  }
+  SAMQ_REQUIRE(workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, SAMQ_ERR_BAD_ARG,
+               "samq_qlinear_fwd: bits=%d%s needs a 16-byte aligned K*N fp16 workspace", bits,
+               g_idx ? " with g_idx" : "");
+  rc = unpack_dequant(qweight, qzeros, scales, g_idx, workspace, K, N, bits, groupsize, 1, st);
+  if (rc != SAMQ_OK) return rc;
+  return launch_qlinear<192, false>(x, workspace, nullptr, nullptr,
+                                    reinterpret_cast<const __half*>(bias),
+                                    reinterpret_cast<const __half*>(residual),
+                                    reinterpret_cast<__half*>(y), M, K, N, K, epilogue, st);
+}

@@ -1,0 +1,179 @@
+"""Tensor-level wrappers over the C ABI (include/samq.h).
+
+Each function validates dtype / contiguity / device on the host (raising the
+exception types the reference raises), allocates the output with torch
+and launches the CUDA kernel on torch's current stream.  No eager fallback exists.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _dev_ctx(t: torch.Tensor):
+    _lib.require_cuda(t, "input")
+    _lib.device_check(t.device)
+    return torch.cuda.device(t.device)
+
+
+def _check_half(t: torch.Tensor, name: str) -> None:
+    assert t.dtype == torch.float16, f"{name} must be float16 (got {t.dtype})"
+    assert t.is_contiguous(), f"{name} must be contiguous"
+
+
+def num_groups(infeatures: int, groupsize: int) -> int:
+    gs = infeatures if groupsize == -1 else groupsize
+    return math.ceil(infeatures / gs)
+
+
+def unpack_dequant(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, bits: int,
+                   groupsize: int, g_idx: Optional[torch.Tensor] = None,
+                   transposed: bool = False) -> torch.Tensor:
+    """Dequantised fp16 weight ``[K, N]`` (or ``[N, K]`` if transposed)."""
+    if bits not in (2, 3, 4, 8):
+        raise NotImplementedError("Only 2, 3, 4 and 8 bits are supported.")
+    assert qweight.dtype == torch.int32 and qzeros.dtype == torch.int32, "qweight/qzeros must be int32"
+    assert qweight.is_contiguous() and qzeros.is_contiguous(), "qweight/qzeros must be contiguous"
+    _check_half(scales, "scales")
+    N = qweight.shape[1]
+    K = qweight.shape[0] * 32 // bits
+    if g_idx is not None:
+        assert g_idx.dtype == torch.int32 and g_idx.numel() == K and g_idx.is_contiguous()
+    with _dev_ctx(qweight):
+        out = torch.empty((N, K) if transposed else (K, N), dtype=torch.float16, device=qweight.device)
+        _lib.check(_lib.load().samq_unpack_dequant(
+            _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx), _lib.ptr(out),
+            K, N, bits, groupsize, 1 if transposed else 0, _lib.stream_ptr(qweight.device)))
+    return out
+
+
+def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
+            bits: int, groupsize: int, bias: Optional[torch.Tensor] = None,
+            g_idx: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_NONE,
+            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``epi(x @ W + bias) + residual`` for a GPTQ-packed W; ``x[..., K]`` fp16 -> ``[..., N]`` fp16."""
+    if bits not in (2, 3, 4, 8):
+        raise NotImplementedError("Only 2, 3, 4 and 8 bits are supported.")
+    _lib.require_cuda(x, "x")
+    assert x.dtype == torch.float16, f"A must be float16 (got {x.dtype})"
+    assert x.is_contiguous(), "A must be contiguous"          # quant_linear.py:381
+    K = x.shape[-1]
+    f_words = qweight.shape[0] * 32 // bits
+    assert K == f_words, "A's last dimension must match the packed weight's infeatures"  # :378-380
+    N = qweight.shape[1]
+    x2 = x.view(-1, K)
+    M = x2.shape[0]
+    if bias is not None:
+        _check_half(bias, "bias")
+        assert bias.numel() == N
+    with _dev_ctx(x):
+        y = out if out is not None else torch.empty(x.shape[:-1] + (N,), dtype=torch.float16, device=x.device)
+        assert y.is_contiguous() and y.dtype == torch.float16 and y.numel() == M * N
+        if residual is not None:
+            _check_half(residual, "residual")
+            assert residual.numel() == M * N
+        if M == 0:
+            return y
+        fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
+        ws = None if fused else torch.empty(K * N, dtype=torch.float16, device=x.device)
+        _lib.check(_lib.load().samq_qlinear_fwd(
+            _lib.ptr(x2), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx),
+            _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), _lib.ptr(ws), M, K, N, bits, groupsize,
+            epilogue, _lib.stream_ptr(x.device)))
+    return y
+
+
+def dense_linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 epilogue: int = _lib.EPI_NONE, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``epi(x @ wt.T + bias) + residual`` with ``wt[N, K]`` fp16 (already dequantised)."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x")
+    _check_half(wt, "wt")
+    N, K = wt.shape
+    assert x.shape[-1] == K
+    x2 = x.view(-1, K)
+    M = x2.shape[0]
+    with _dev_ctx(x):
+        y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float16, device=x.device)
+        if M == 0:
+            return y
+        _lib.check(_lib.load().samq_dense_linear_fwd(
+            _lib.ptr(x2), _lib.ptr(wt), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), M, K, N,
+            epilogue, _lib.stream_ptr(x.device)))
+    return y
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x"); _check_half(weight, "weight"); _check_half(bias, "bias")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    with _dev_ctx(x):
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().samq_layernorm_fwd(
+            _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), rows, C, float(eps),
+            _lib.stream_ptr(x.device)))
+    return y
+
+
+def layernorm_partition(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float,
+                        window_size: int) -> Tuple[torch.Tensor, Tuple[int, int]]:
+    """LayerNorm + window_partition: ``[B,H,W,C]`` -> ``([B*nWin, ws, ws, C], (Hp, Wp))``."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x"); _check_half(weight, "weight"); _check_half(bias, "bias")
+    B, H, W, C = x.shape
+    ws = window_size
+    nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
+    with _dev_ctx(x):
+        y = torch.empty((B * nH * nW, ws, ws, C), dtype=torch.float16, device=x.device)
+        _lib.check(_lib.load().samq_layernorm_partition_fwd(
+            _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(y), B, H, W, C, ws, float(eps),
+            _lib.stream_ptr(x.device)))
+    return y, (nH * ws, nW * ws)
+
+
+def unpartition_residual(windows: torch.Tensor, shortcut: torch.Tensor, window_size: int) -> torch.Tensor:
+    """``shortcut + window_unpartition(windows)`` -> ``[B,H,W,C]``."""
+    _lib.require_cuda(windows, "windows")
+    _check_half(windows, "windows"); _check_half(shortcut, "shortcut")
+    B, H, W, C = shortcut.shape
+    with _dev_ctx(windows):
+        out = torch.empty_like(shortcut)
+        _lib.check(_lib.load().samq_unpartition_residual(
+            _lib.ptr(windows), _lib.ptr(shortcut), _lib.ptr(out), B, H, W, C, window_size,
+            _lib.stream_ptr(windows.device)))
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda(a, "a")
+    _check_half(a, "a"); _check_half(b, "b")
+    assert a.shape == b.shape
+    with _dev_ctx(a):
+        out = torch.empty_like(a)
+        _lib.check(_lib.load().samq_add(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), a.numel(),
+                                        _lib.stream_ptr(a.device)))
+    return out
+
+
+def attn_relpos(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, B: int, H: int,
+                W: int, num_heads: int, scale: float, relw_mode: int = _lib.RELW_REFERENCE) -> torch.Tensor:
+    """Fused attention on the packed qkv GEMM output ``[B, H*W, 3*heads*hd]`` -> ``[B, H, W, heads*hd]``."""
+    _lib.require_cuda(qkv, "qkv")
+    _check_half(qkv, "qkv"); _check_half(rel_pos_h, "rel_pos_h"); _check_half(rel_pos_w, "rel_pos_w")
+    D3 = qkv.shape[-1]
+    assert D3 % (3 * num_heads) == 0
+    hd = D3 // 3 // num_heads
+    assert qkv.numel() == B * H * W * D3
+    assert rel_pos_h.shape == (2 * H - 1, hd) and rel_pos_w.shape == (2 * W - 1, hd), \
+        "rel_pos tables must be [2*size-1, head_dim] (no interpolation path)"
+    with _dev_ctx(qkv):
+        out = torch.empty((B, H, W, num_heads * hd), dtype=torch.float16, device=qkv.device)
+        _lib.check(_lib.load().samq_attn_relpos_fwd(
+            _lib.ptr(qkv), _lib.ptr(rel_pos_h), _lib.ptr(rel_pos_w), _lib.ptr(out), B, H, W,
+            num_heads, hd, float(scale), relw_mode, _lib.stream_ptr(qkv.device)))
+    return out
