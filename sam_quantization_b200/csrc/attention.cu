@@ -1,8 +1,498 @@
-// placeholder until the tcgen05 attention kernel lands (next commit)
+// Flash-style attention with SAM's decomposed relative-position bias on sm_100a.
+//
+// Replaces QuantAttention.forward's q-slice copy, add_decomposed_rel_pos (2 x
+// get_rel_pos + 2 batched matmuls through HBM) and the Triton kernel _fwd_kernel1
+// (gptq_triton/fused_attention.py:46-80, 107-133, 159-358).
+//
+//   out[b, m, head, :] = softmax_n( scale * q[m].k[n] + rel_h[m, n / E] + rel_w[m, n % E] ) v[n]
+//   rel_h[m, kh] = fp16( q[m] . rel_pos_h[h(m) - kh + E-1] )
+//   rel_w[m, kw] = fp16( q[m] . rel_pos_w[r(m) - kw + E-1] ),  r(m) = h(m) in "reference"
+//                  mode (the fork's matmul broadcasting, fused_attention.py:76-78)
+//                  or w(m) in "upstream" mode.
+//
+// One CTA = one (batch/window, head, 128-query tile).  tcgen05 everywhere:
+//   prologue: T_h = Q . rel_pos_h^T, T_w = Q . rel_pos_w^T  (two MMAs into the S
+//             buffers), rounded to fp16 and bounced through shared memory so each
+//             softmax thread (= one query row) can gather its E + E bias values;
+//   loop    : S_j = Q . K_j^T (SS MMA, fp32 in TMEM, double buffered)
+//             softmax threads read S_j from TMEM (one row per thread: no shuffles),
+//             add bias, online softmax in base 2 (fused_attention.py:219,275-293)
+//             with lazy rescaling, write P_j as fp16 back into the S_j columns
+//             O += P_j . V_j (TS MMA: P from TMEM, V tile MN-major in shared memory)
+//   epilogue: O / l -> fp16 -> [B, S, heads*hd].
+// head_dim 80 is handled without padding to 128 (the reference pads,
+// fused_attention.py:323): K = 64 (128B-swizzle tile) + 16 (32B-swizzle tile).
 #include "common.cuh"
+
+namespace samq {
+namespace {
+
+constexpr int kAttThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int HD, bool WIN>
+struct ACfg {
+  static constexpr int E = WIN ? 14 : 64;           // H == W
+  static constexpr int S = E * E;                   // tokens per image / window
+  static constexpr int kQTiles = (S + 127) / 128;
+  static constexpr int kKVTiles = (S + 127) / 128;
+  static constexpr int kTail = HD - 64;             // 0 or 16
+  static constexpr int kMainBytes = 128 * 128;      // 128 rows x 64 fp16, 128B swizzle
+  static constexpr int kTailBytes = kTail ? 128 * 32 : 0;  // 128 rows x 16 fp16, 32B swizzle
+  static constexpr int kTileBytes = kMainBytes + kTailBytes;
+  static constexpr int kRpRows = WIN ? 32 : 128;    // rel-pos table rows (2E-1) padded
+  static constexpr int kRpMainBytes = kRpRows * 128;
+  static constexpr int kRpTailBytes = kTail ? kRpRows * 32 : 0;
+  static constexpr int kRpBytes = kRpMainBytes + kRpTailBytes;
+  static constexpr int kStages = (HD == 64) ? 3 : 2;
+  static constexpr int kBounceWords = WIN ? 17 : 65;  // row stride (32-bit words), odd: conflict-free
+  static constexpr int kBounceBytes = ((128 * kBounceWords * 4 + 1023) / 1024) * 1024;
+  // shared memory carve (all tile bases 1024-aligned)
+  static constexpr int oQ = 0;
+  static constexpr int oRph = oQ + kTileBytes;
+  static constexpr int oRpw = oRph + ((kRpBytes + 1023) / 1024) * 1024;
+  static constexpr int oKV = oRpw + ((kRpBytes + 1023) / 1024) * 1024;
+  static constexpr int oTh = oKV + kStages * 2 * kTileBytes;
+  static constexpr int oTw = oTh + kBounceBytes;
+  static constexpr int oBars = oTw + kBounceBytes;
+  static constexpr int kNumBars = 1 + 2 * kStages + 2 + 2 + 2 + 2;
+  static constexpr int kSmemBytes = oBars + kNumBars * 8 + 16 + 1024;
+  // TMEM columns
+  static constexpr int cS0 = 0, cS1 = 128, cO = 256;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int HD, bool WIN>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
+                   const __grid_constant__ CUtensorMap map_qkv_tail,
+                   const __grid_constant__ CUtensorMap map_rph_main,
+                   const __grid_constant__ CUtensorMap map_rph_tail,
+                   const __grid_constant__ CUtensorMap map_rpw_main,
+                   const __grid_constant__ CUtensorMap map_rpw_tail, __half* __restrict__ out,
+                   int heads, float scale, int relw_mode) {
+  using C = ACfg<HD, WIN>;
+  constexpr int E = C::E, S = C::S, T = C::kKVTiles;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem + C::oQ;
+  uint8_t* sRph = smem + C::oRph;
+  uint8_t* sRpw = smem + C::oRpw;
+  uint8_t* sKV = smem + C::oKV;
+  uint32_t* sTh = reinterpret_cast<uint32_t*>(smem + C::oTh);
+  uint32_t* sTw = reinterpret_cast<uint32_t*>(smem + C::oTw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBars);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = q_full + 1;
+  uint64_t* kv_empty = kv_full + C::kStages;
+  uint64_t* t_full = kv_empty + C::kStages;
+  uint64_t* t_done = t_full + 1;
+  uint64_t* s_full = t_done + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int D = heads * HD;
+  const int m0 = q_tile * 128;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_done, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_qkv_main);
+    tma_prefetch_desc(&map_rph_main);
+    tma_prefetch_desc(&map_rpw_main);
+    if (C::kTail) {
+      tma_prefetch_desc(&map_qkv_tail);
+      tma_prefetch_desc(&map_rph_tail);
+      tma_prefetch_desc(&map_rpw_tail);
+    }
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, C::kTileBytes + 2 * C::kRpBytes);
+      tma_load_3d(sQ, &map_qkv_main, q_full, head * HD, m0, b);
+      tma_load_2d(sRph, &map_rph_main, q_full, 0, 0);
+      tma_load_2d(sRpw, &map_rpw_main, q_full, 0, 0);
+      if (C::kTail) {
+        tma_load_3d(sQ + C::kMainBytes, &map_qkv_tail, q_full, head * HD + 64, m0, b);
+        tma_load_2d(sRph + C::kRpMainBytes, &map_rph_tail, q_full, 64, 0);
+        tma_load_2d(sRpw + C::kRpMainBytes, &map_rpw_tail, q_full, 64, 0);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * C::kTileBytes);
+        uint8_t* sK = sKV + s * 2 * C::kTileBytes;
+        uint8_t* sV = sK + C::kTileBytes;
+        tma_load_3d(sK, &map_qkv_main, &kv_full[s], D + head * HD, j * 128, b);
+        tma_load_3d(sV, &map_qkv_main, &kv_full[s], 2 * D + head * HD, j * 128, b);
+        if (C::kTail) {
+          tma_load_3d(sK + C::kMainBytes, &map_qkv_tail, &kv_full[s], D + head * HD + 64, j * 128, b);
+          tma_load_3d(sV + C::kMainBytes, &map_qkv_tail, &kv_full[s], 2 * D + head * HD + 64, j * 128, b);
+        }
+        if (++s == C::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0);
+      constexpr uint32_t idesc_t = make_idesc_f16(128, C::kRpRows, 0);
+      constexpr uint32_t idesc_pv_main = make_idesc_f16(128, 64, 1);
+      constexpr uint32_t idesc_pv_tail = make_idesc_f16(128, 16, 1);
+      const uint64_t q_main = make_smem_desc(smem_u32(sQ), 0, 1024, kLayoutSw128);
+      const uint64_t q_tail = make_smem_desc(smem_u32(sQ + C::kMainBytes), 0, 256, kLayoutSw32);
+
+      // S_buf = Q . B^T for a K-major B tile (K tile or rel-pos table)
+      auto mma_q_times = [&](uint32_t d_tmem, const uint8_t* b_main_ptr, const uint8_t* b_tail_ptr,
+                             uint32_t idesc) {
+        const uint64_t b_main = make_smem_desc(smem_u32(b_main_ptr), 0, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc, k > 0);
+        if (C::kTail) {
+          const uint64_t b_tail = make_smem_desc(smem_u32(b_tail_ptr), 0, 256, kLayoutSw32);
+          tc_mma_ss(d_tmem, q_tail, b_tail, idesc, 1);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      mma_q_times(tmem_base + C::cS0, sRph, sRph + C::kRpMainBytes, idesc_t);
+      mma_q_times(tmem_base + C::cS1, sRpw, sRpw + C::kRpMainBytes, idesc_t);
+      tc_commit(t_full);
+
+      mbar_wait(&kv_full[0], 0);
+      mbar_wait(t_done, 0);  // softmax threads have copied T_h / T_w out of the S buffers
+      tc_fence_after();
+      mma_q_times(tmem_base + C::cS0, sKV, sKV + C::kMainBytes, idesc_qk);
+      tc_commit(&s_full[0]);
+
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          int s1 = s + 1;
+          uint32_t ph1 = ph;
+          if (s1 == C::kStages) { s1 = 0; ph1 ^= 1; }
+          mbar_wait(&kv_full[s1], ph1);
+          tc_fence_after();
+          const uint8_t* sK1 = sKV + s1 * 2 * C::kTileBytes;
+          // in-order tensor pipe: this overwrite of S[(j+1)&1] is ordered after PV(j-1)
+          mma_q_times(tmem_base + (((j + 1) & 1) ? C::cS1 : C::cS0), sK1, sK1 + C::kMainBytes, idesc_qk);
+          tc_commit(&s_full[(j + 1) & 1]);
+        }
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint8_t* sV = sKV + s * 2 * C::kTileBytes + C::kTileBytes;
+        const uint32_t p_tmem = tmem_base + ((j & 1) ? C::cS1 : C::cS0);
+        const int keys = (S - j * 128) < 128 ? (S - j * 128) : 128;
+        const int ksteps = (keys + 15) / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          const uint64_t v_main = make_smem_desc(smem_u32(sV + ks * 2048), C::kMainBytes, 1024, kLayoutSw128);
+          tc_mma_ts(tmem_base + C::cO, p_tmem + ks * 8, v_main, idesc_pv_main, acc);
+          if (C::kTail) {
+            const uint64_t v_tail =
+                make_smem_desc(smem_u32(sV + C::kMainBytes + ks * 512), C::kTailBytes, 256, kLayoutSw32);
+            tc_mma_ts(tmem_base + C::cO + 64, p_tmem + ks * 8, v_tail, idesc_pv_tail, acc);
+          }
+        }
+        tc_commit(&kv_empty[s]);
+        tc_commit(&pv_done[j & 1]);
+        if (++s == C::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ softmax / epilogue ============================
+    const int e = warp - 4;
+    const int row = e * 32 + lane;            // query row in tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(e * 32) << 16;
+    const int m = m0 + row;
+    const bool valid = m < S;
+    const int mh = valid ? m / E : 0, mw = valid ? m % E : 0;
+    const float c_scale = scale * kLog2e;
+
+    // ---- rel-pos tables: TMEM -> fp16 -> shared (own row only) ----
+    mbar_wait(t_full, 0);
+    tc_fence_after();
+    uint32_t* my_th = sTh + row * C::kBounceWords;
+    uint32_t* my_tw = sTw + row * C::kBounceWords;
+#pragma unroll
+    for (int c = 0; c < C::kRpRows / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_base + C::cS0 + c * 32 + lane_off, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        my_th[c * 16 + i] = pack_h2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+      tmem_ld_x32(tmem_base + C::cS1 + c * 32 + lane_off, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        my_tw[c * 16 + i] = pack_h2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t_done);
+
+    const __half* th_row = reinterpret_cast<const __half*>(my_th);
+    const __half* tw_row = reinterpret_cast<const __half*>(my_tw);
+    const int rw = (relw_mode == SAMQ_RELW_UPSTREAM) ? mw : mh;
+    float bw[E];   // log2e * rel_w[m, kw]
+#pragma unroll
+    for (int kw = 0; kw < E; ++kw) bw[kw] = kLog2e * __half2float(tw_row[rw - kw + E - 1]);
+    float bh_win[WIN ? E : 1];  // windowed: log2e * rel_h[m, kh] for all kh
+    if (WIN) {
+#pragma unroll
+      for (int kh = 0; kh < E; ++kh) bh_win[kh] = kLog2e * __half2float(th_row[mh - kh + E - 1]);
+    }
+
+    float m_used = -INFINITY, l = 0.f;
+    // windowed: 2 tiles, fully unrolled so key -> (kh, kw) is resolved at compile time
+#pragma unroll(WIN ? 2 : 1)
+    for (int j = 0; j < T; ++j) {
+      const uint32_t s_tmem = tmem_base + ((j & 1) ? C::cS1 : C::cS0) + lane_off;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float bh0 = 0.f, bh1 = 0.f;
+      if (!WIN) {
+        bh0 = kLog2e * __half2float(th_row[mh - 2 * j + E - 1]);
+        bh1 = kLog2e * __half2float(th_row[mh - 2 * j - 1 + E - 1]);
+      }
+      // ---- pass 1: tile maximum ----
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(s_tmem + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = j * 128 + c * 32 + i;  // key index (compile-time in WIN mode)
+          if (WIN) {
+            if (n < S) mx0 = fmaxf(mx0, fmaf(__uint_as_float(r[i]), c_scale, bh_win[(n / E) % E] + bw[n % E]));
+          } else {
+            const float x = fmaf(__uint_as_float(r[i]), c_scale, bw[(c * 32 + i) % E]);
+            if (c < 2) mx0 = fmaxf(mx0, x); else mx1 = fmaxf(mx1, x);
+          }
+        }
+      }
+      const float m_tile = WIN ? mx0 : fmaxf(mx0 + bh0, mx1 + bh1);
+      const float m_new = fmaxf(m_used, m_tile);
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, m_new > m_used + 8.f)) {
+        // lazy rescale of the running output (rare once the maximum has settled)
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const float alpha = ex2(m_used - m_new);
+        l *= alpha;
+        m_used = m_new;
+        const uint32_t o_tmem = tmem_base + C::cO + lane_off;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(o_tmem + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x32(o_tmem + c * 32, r);
+        }
+        if (C::kTail) {
+          uint32_t r[16];
+          tmem_ld_x16(o_tmem + 64, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x16(o_tmem + 64, r);
+        }
+        tmem_st_wait();
+      }
+      // ---- pass 2: P = 2^(x - m) as fp16 into the S columns, row sum ----
+      const float mm0 = m_used - bh0, mm1 = m_used - bh1;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(s_tmem + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int n = j * 128 + c * 32 + i + u;
+            if (WIN) {
+              p[u] = (n < S) ? ex2(fmaf(__uint_as_float(r[i + u]), c_scale, bh_win[(n / E) % E] + bw[n % E]) - m_used)
+                             : 0.f;
+            } else {
+              const float x = fmaf(__uint_as_float(r[i + u]), c_scale, bw[(c * 32 + i + u) % E]);
+              p[u] = ex2(x - (c < 2 ? mm0 : mm1));
+            }
+            sum += p[u];
+          }
+          pk[i >> 1] = pack_h2(p[0], p[1]);
+        }
+        tmem_st_x16(s_tmem + c * 16, pk);
+      }
+      l += sum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+
+    // ---- epilogue: O / l ----
+    mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const uint32_t o_tmem = tmem_base + C::cO + lane_off;
+    __half* dst = out + (static_cast<size_t>(b) * S + (valid ? m : 0)) * D + head * HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(o_tmem + c * 32, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 o;
+          o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+          o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+          o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+          o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + v * 8) = o;
+        }
+      }
+    }
+    if (C::kTail) {
+      uint32_t r[16];
+      tmem_ld_x16(o_tmem + 64, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          uint4 o;
+          o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+          o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+          o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+          o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + 64 + v * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HD, bool WIN>
+int launch_attn(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads,
+                float scale, int relw_mode, cudaStream_t st) {
+  using C = ACfg<HD, WIN>;
+  const int D = heads * HD;
+  const uint64_t row_bytes = static_cast<uint64_t>(3) * D * 2;
+  uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {row_bytes, row_bytes * C::S};
+  uint32_t box_main[3] = {64, 128, 1};
+  uint32_t box_tail[3] = {16, 128, 1};
+  const CUtensorMap* m_main = get_tensor_map_nd(qkv, 3, dims, strides, box_main, 2, 3);
+  if (!m_main) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap* m_tail = m_main;
+  const int rp_rows = 2 * C::E - 1;
+  const CUtensorMap* h_main = get_tensor_map_2d(rph, rp_rows, HD, HD * 2, C::kRpRows, 64, 2, 3);
+  const CUtensorMap* w_main = get_tensor_map_2d(rpw, rp_rows, HD, HD * 2, C::kRpRows, 64, 2, 3);
+  if (!h_main || !w_main) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap* h_tail = h_main;
+  const CUtensorMap* w_tail = w_main;
+  if (C::kTail) {
+    m_tail = get_tensor_map_nd(qkv, 3, dims, strides, box_tail, 2, 1);
+    h_tail = get_tensor_map_2d(rph, rp_rows, HD, HD * 2, C::kRpRows, 16, 2, 1);
+    w_tail = get_tensor_map_2d(rpw, rp_rows, HD, HD * 2, C::kRpRows, 16, 2, 1);
+    if (!m_tail || !h_tail || !w_tail) return SAMQ_ERR_LAUNCH;
+  }
+  auto kern = attn_relpos_kernel<HD, WIN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
+      return SAMQ_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  dim3 grid(C::kQTiles, heads, B);
+  kern<<<grid, kAttThreads, C::kSmemBytes, st>>>(*m_main, *m_tail, *h_main, *h_tail, *w_main, *w_tail,
+                                                reinterpret_cast<__half*>(out), heads, scale, relw_mode);
+  count_launch();
+  return check_launch("attn_relpos_kernel");
+}
+
+}  // namespace
+}  // namespace samq
+
 extern "C" int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
                                     void* out, int B, int H, int W, int heads, int hd, float scale,
                                     int relw_mode, void* stream) {
-  samq::set_error("samq_attn_relpos_fwd: not built yet");
-  return SAMQ_ERR_LAUNCH;
+  using namespace samq;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMQ_REQUIRE(qkv && rel_pos_h && rel_pos_w && out, SAMQ_ERR_BAD_ARG, "samq_attn_relpos_fwd: null pointer");
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(rel_pos_h) |
+                reinterpret_cast<uintptr_t>(rel_pos_w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "samq_attn_relpos_fwd: pointers must be 16-byte aligned");
+  SAMQ_REQUIRE(relw_mode == SAMQ_RELW_REFERENCE || relw_mode == SAMQ_RELW_UPSTREAM, SAMQ_ERR_BAD_ARG,
+               "samq_attn_relpos_fwd: bad relw_mode %d", relw_mode);
+  SAMQ_REQUIRE(B > 0 && B <= 65535 && heads > 0 && heads <= 65535, SAMQ_ERR_BAD_SHAPE,
+               "samq_attn_relpos_fwd: B=%d heads=%d out of range", B, heads);
+  SAMQ_REQUIRE(hd == 64 || hd == 80, SAMQ_ERR_BAD_SHAPE,
+               "samq_attn_relpos_fwd: head_dim %d not supported (64 or 80)", hd);
+  const bool glob = (H == 64 && W == 64), win = (H == 14 && W == 14);
+  SAMQ_REQUIRE(glob || win, SAMQ_ERR_BAD_SHAPE,
+               "samq_attn_relpos_fwd: (H,W)=(%d,%d) not supported ((64,64) or (14,14))", H, W);
+  if (hd == 64) {
+    return glob ? launch_attn<64, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
+                : launch_attn<64, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+  }
+  return glob ? launch_attn<80, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
+              : launch_attn<80, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
 }

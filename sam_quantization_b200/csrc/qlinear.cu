@@ -50,8 +50,9 @@ struct Cfg {
   static constexpr int kTmemABase = 2 * BM;                 // column offset of A stages
   static constexpr int kSmemData =
       kXStages * kXStageBytes + (FUSED ? kWStages * kWStageBytes : kXStages * kAStageBytes);
+  static constexpr int kEpiBytes = 4 * 2048;  // one 32x32 fp16 transpose block per epilogue warp
   static constexpr int kNumBars = 2 * kXStages + 2 * kWStages + 2 * 8 + 4;
-  static constexpr int kSmemBytes = kSmemData + kNumBars * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int kSmemBytes = kSmemData + kEpiBytes + kNumBars * 8 + 16 + 1024;  // + alignment slack
   static_assert(kAStages >= 2 || !FUSED, "need at least two TMEM A stages");
   static_assert(BM % 32 == 0 && BM <= 256, "BM");
 };
@@ -91,7 +92,8 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sx = smem;
   uint8_t* sw = sx + C::kXStages * C::kXStageBytes;  // fused: packed W ring; dense: Wt ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemData);
+  uint8_t* sepi = smem + C::kSmemData;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kSmemData + C::kEpiBytes);
   uint64_t* x_full = bars;
   uint64_t* x_empty = x_full + C::kXStages;
   uint64_t* w_full = x_empty + C::kXStages;
@@ -294,6 +296,10 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       mbar_wait(&acc_full[ab], acc_ph);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * BM + (static_cast<uint32_t>(e * 32) << 16);
+      // 32(m) x 32(n) staging block of this warp: lanes own n, so the block is
+      // transposed through shared memory and written as 16-byte row segments
+      // (2-byte scattered global stores ran at <2 B/clk/SM).
+      __half* stage = reinterpret_cast<__half*>(sepi + e * 2048);
 #pragma unroll 1
       for (int c = 0; c < BM / 32; ++c) {
         uint32_t r[32];
@@ -305,18 +311,33 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
-        const int m0 = m_tile * BM + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int m = m0 + j;
+          float v = __uint_as_float(r[j]) + bv;
+          if (epilogue == SAMQ_EPI_GELU) v = gelu_erf(v);
+          stage[j * 32 + lane] = __float2half_rn(v);
+        }
+        __syncwarp();
+        const int m0 = m_tile * BM + c * 32;
+        const int q = lane & 3;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + (lane >> 2);
+          const int m = m0 + row;
           if (m < M) {
-            float v = __uint_as_float(r[j]) + bv;
-            if (epilogue == SAMQ_EPI_GELU) v = gelu_erf(v);
-            const size_t off = static_cast<size_t>(m) * N + n;
-            if (residual) v += __half2float(residual[off]);
-            y[off] = __float2half_rn(v);
+            uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + q * 8);
+            const size_t off = static_cast<size_t>(m) * N + (n_tile * kBN + e * 32 + q * 8);
+            if (residual) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(residual + off);
+              val.x = h2_add(val.x, rv.x);
+              val.y = h2_add(val.y, rv.y);
+              val.z = h2_add(val.z, rv.z);
+              val.w = h2_add(val.w, rv.w);
+            }
+            *reinterpret_cast<uint4*>(y + off) = val;
           }
         }
+        __syncwarp();
       }
     }
   }

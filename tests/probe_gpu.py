@@ -125,9 +125,54 @@ def probe_fused():
             ms = e0.elapsed_time(e1) / 20
             print(f"fused M={M} K={K} N={N} epi={epi}: {ms*1e3:.1f} us  {2*M*K*N/ms/1e9:.1f} TFLOP/s")
 
+def attn_ref(qkv, rph, rpw, B, E, heads, scale, upstream=False):
+    S = E * E
+    hd = qkv.shape[-1] // 3 // heads
+    x = qkv.float().view(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, B * heads, S, hd)
+    q, k, v = x[0], x[1], x[2]
+    idx = (torch.arange(E)[:, None] - torch.arange(E)[None, :] + (E - 1)).to(qkv.device)
+    Rh = rph.float()[idx]; Rw = rpw.float()[idx]
+    r_q = q.view(B * heads, E, E, hd)
+    rel_h = torch.einsum("bhwc,hkc->bhwk", r_q, Rh).half().float()
+    rel_w = torch.einsum("bhwc,wkc->bhwk" if upstream else "bhwc,hkc->bhwk", r_q, Rw).half().float()
+    attn = (q * scale) @ k.transpose(-2, -1)
+    attn = (attn.view(B * heads, E, E, E, E) + rel_h[..., :, None] + rel_w[..., None, :]).view(B * heads, S, S)
+    attn = attn.softmax(-1)
+    return (attn @ v).view(B, heads, E, E, hd).permute(0, 2, 3, 1, 4).reshape(B, E, E, heads * hd)
+
+def probe_attn():
+    torch.manual_seed(20)
+    for (B, E, heads, hd) in [(3, 14, 2, 64), (3, 14, 2, 80), (1, 64, 2, 64), (1, 64, 2, 80), (25, 14, 16, 80), (1, 64, 16, 80), (2, 64, 12, 64)]:
+        for upstream in (False, True):
+            qkv = (torch.randn(B, E * E, 3 * heads * hd, device=dev) * 0.5).half()
+            rph = (torch.randn(2 * E - 1, hd, device=dev) * 0.3).half()
+            rpw = (torch.randn(2 * E - 1, hd, device=dev) * 0.3).half()
+            scale = hd ** -0.5
+            out = ops.attn_relpos(qkv, rph, rpw, B, E, E, heads, scale, 1 if upstream else 0)
+            torch.cuda.synchronize()
+            ref = attn_ref(qkv, rph, rpw, B, E, heads, scale, upstream)
+            d = (out.float() - ref).abs()
+            cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item()
+            print(f"attn B={B} E={E} heads={heads} hd={hd} upstream={upstream}: maxabs {d.max().item():.4e} refmax {ref.abs().max().item():.3f} cos {cos:.7f} nan {torch.isnan(out).sum().item()}", flush=True)
+            if not cos > 0.999:
+                bad = (d > 0.05).float().view(B, E * E, heads, hd)
+                print("   bad frac", bad.mean().item(), "by head", bad.mean((0, 1, 3)).tolist()[:4], "by d (first 8, last 8)", bad.mean((0, 1, 2))[:8].tolist(), bad.mean((0, 1, 2))[-8:].tolist())
+                print("   bad by row-block of 32:", bad.mean((0, 2, 3)).view(-1, 32).mean(1)[:8].tolist())
+    for (B, E, heads, hd) in [(8, 64, 16, 80), (200, 14, 16, 80), (8, 64, 16, 64), (200, 14, 16, 64)]:
+        qkv = (torch.randn(B, E * E, 3 * heads * hd, device=dev) * 0.5).half()
+        rph = (torch.randn(2 * E - 1, hd, device=dev) * 0.3).half(); rpw = (torch.randn(2 * E - 1, hd, device=dev) * 0.3).half()
+        for _ in range(3): ops.attn_relpos(qkv, rph, rpw, B, E, E, heads, hd ** -0.5)
+        torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): ops.attn_relpos(qkv, rph, rpw, B, E, E, heads, hd ** -0.5)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = 4 * (E * E) ** 2 * hd * heads * B
+        print(f"attn B={B} E={E} heads={heads} hd={hd}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s")
+
 if __name__ == "__main__":
     which = sys.argv[1]
     print("=== probe", which, torch.cuda.get_device_name(0), flush=True)
-    {"dequant": probe_dequant, "ln": probe_ln, "dense": probe_dense, "fused": probe_fused}[which]()
+    {"dequant": probe_dequant, "ln": probe_ln, "dense": probe_dense, "fused": probe_fused, "attn": probe_attn}[which]()
     torch.cuda.synchronize()
     print("=== done", which)
