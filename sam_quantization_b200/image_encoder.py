@@ -1,0 +1,291 @@
+"""Host module for the SAM ViT image encoder that the quantized operators drop into.
+
+Mirrors the module tree, parameter names and forward semantics of
+/root/reference/segment_anything/modeling/image_encoder.py:17-442 and
+common.py:13-43 (so reference / upstream checkpoints load by key), written for the
+fused B200 path:
+
+  * ``window_partition`` / ``window_unpartition`` are the GENERIC formulas (the fork
+    hard-codes ViT-H, batch 1: image_encoder.py:297-305, 324-332; generic form:
+    fq_vit/models/sam/image_encoder.py:481-537) -- and on the fused path they are not
+    separate ops at all: partition is fused into LayerNorm, unpartition + crop into the
+    residual add.
+  * ``Block.forward`` (image_encoder.py:189-207) has a fused CUDA path used whenever the
+    block is quantized and fed fp16 CUDA tensors:
+        LN1(+partition) -> qkv dequant-GEMM -> attention(+rel-pos) -> proj dequant-GEMM
+        (+residual | unpartition+residual) -> LN2 -> lin1 dequant-GEMM(+bias+GELU)
+        -> lin2 dequant-GEMM(+bias+residual)
+    i.e. 7 kernels per block, no eager elementwise op.
+  * Before quantization (fp32/fp16 nn.Linear) the module runs plain PyTorch, which is
+    how weights are calibrated / packed and how the CPU tests drive the host logic.
+    That eager path is NOT a fallback of the quantized path: a quantized block on a
+    non-CUDA tensor raises.
+
+Patch embedding and neck (0.26 % of FLOPs) stay on cuDNN/ATen.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Type
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .fused_attention import QuantAttention
+from .fused_mlp import QuantMLP
+from .quant_linear import QuantLinear
+
+__all__ = [
+    "ImageEncoderViT", "Block", "Attention", "MLPBlock", "PatchEmbed", "LayerNorm2d",
+    "window_partition", "window_unpartition", "get_rel_pos", "decomposed_rel_pos",
+    "ENCODER_CONFIGS", "build_image_encoder",
+]
+
+# build_sam.py:14-44 (shapes), :67-80 (shared settings)
+ENCODER_CONFIGS = {
+    "vit_h": dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31)),
+    "vit_l": dict(embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23)),
+    "vit_b": dict(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
+}
+
+
+def build_image_encoder(name: str = "vit_h", **overrides) -> "ImageEncoderViT":
+    """SAM image encoder with the registry's settings (build_sam.py:55-80): img 1024,
+    patch 16, mlp_ratio 4, LayerNorm eps 1e-6, qkv_bias, rel-pos, window 14, out 256."""
+    cfg = dict(ENCODER_CONFIGS[name])
+    cfg.update(img_size=1024, patch_size=16, mlp_ratio=4.0, out_chans=256, qkv_bias=True,
+               use_rel_pos=True, window_size=14, norm_eps=1e-6)
+    cfg.update(overrides)
+    return ImageEncoderViT(**cfg)
+
+
+class LayerNorm2d(nn.Module):
+    """Channel-wise LayerNorm over NCHW (common.py:31-43)."""
+
+    def __init__(self, num_channels: int, eps: float = 1e-6) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(num_channels))
+        self.bias = nn.Parameter(torch.zeros(num_channels))
+        self.eps = eps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        mean = x.mean(1, keepdim=True)
+        var = (x - mean).pow(2).mean(1, keepdim=True)
+        x = (x - mean) / torch.sqrt(var + self.eps)
+        return self.weight[:, None, None] * x + self.bias[:, None, None]
+
+
+class MLPBlock(nn.Module):
+    """lin2(act(lin1(x))) (common.py:13-26)."""
+
+    def __init__(self, embedding_dim: int, mlp_dim: int, act: Type[nn.Module] = nn.GELU) -> None:
+        super().__init__()
+        self.lin1 = nn.Linear(embedding_dim, mlp_dim)
+        self.lin2 = nn.Linear(mlp_dim, embedding_dim)
+        self.act = act()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.lin2(self.act(self.lin1(x)))
+
+
+class PatchEmbed(nn.Module):
+    """conv16x16/16 then NCHW -> NHWC (image_encoder.py:411-442)."""
+
+    def __init__(self, kernel_size=(16, 16), stride=(16, 16), padding=(0, 0), in_chans: int = 3,
+                 embed_dim: int = 768) -> None:
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride,
+                              padding=padding)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.proj(x).permute(0, 2, 3, 1)
+
+
+def window_partition(x: torch.Tensor, window_size: int) -> Tuple[torch.Tensor, Tuple[int, int]]:
+    """[B,H,W,C] -> ([B*nWin, ws, ws, C], (Hp, Wp)), zero padding bottom/right.
+    Generic form (fq_vit/models/sam/image_encoder.py:481-507); equals the fork's
+    hard-coded version for ViT-H, batch 1 (image_encoder.py:282-306)."""
+    B, H, W, C = x.shape
+    pad_h = (window_size - H % window_size) % window_size
+    pad_w = (window_size - W % window_size) % window_size
+    if pad_h or pad_w:
+        x = F.pad(x, (0, 0, 0, pad_w, 0, pad_h))
+    Hp, Wp = H + pad_h, W + pad_w
+    x = x.view(B, Hp // window_size, window_size, Wp // window_size, window_size, C)
+    windows = x.permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, window_size, window_size, C)
+    return windows, (Hp, Wp)
+
+
+def window_unpartition(windows: torch.Tensor, window_size: int, pad_hw: Tuple[int, int],
+                       hw: Tuple[int, int]) -> torch.Tensor:
+    """Inverse of ``window_partition`` + crop (fq_vit/.../image_encoder.py:510-537)."""
+    Hp, Wp = pad_hw
+    H, W = hw
+    B = windows.shape[0] // (Hp * Wp // window_size // window_size)
+    x = windows.view(B, Hp // window_size, Wp // window_size, window_size, window_size, -1)
+    x = x.permute(0, 1, 3, 2, 4, 5).contiguous().view(B, Hp, Wp, -1)
+    if Hp > H or Wp > W:
+        x = x[:, :H, :W, :].contiguous()
+    return x
+
+
+def get_rel_pos(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tensor:
+    """R[i, j, :] = rel_pos[i - j + (k_size - 1)] for the square, non-interpolated case
+    SAM uses (image_encoder.py:336-366: table length is 2*size-1, :246-247)."""
+    if q_size != k_size or rel_pos.shape[0] != 2 * q_size - 1:
+        raise NotImplementedError("only square windows with a 2*size-1 table (SAM's case)")
+    idx = torch.arange(q_size, device=rel_pos.device)[:, None] - \
+        torch.arange(k_size, device=rel_pos.device)[None, :] + (k_size - 1)
+    return rel_pos[idx]
+
+
+def decomposed_rel_pos(q: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor,
+                       hw: Tuple[int, int], relw_mode: str = "reference"):
+    """(rel_h, rel_w), each [B', H, W, k] (image_encoder.py:369-408).  In "reference" mode
+    rel_w uses the fork's matmul broadcasting (row-indexed Rw, image_encoder.py:401-402)."""
+    H, W = hw
+    Rh = get_rel_pos(H, H, rel_pos_h)
+    Rw = get_rel_pos(W, W, rel_pos_w)
+    r_q = q.reshape(q.shape[0], H, W, q.shape[-1])
+    rel_h = torch.einsum("bhwc,hkc->bhwk", r_q, Rh)
+    rel_w = torch.einsum("bhwc,hkc->bhwk" if relw_mode == "reference" else "bhwc,wkc->bhwk", r_q, Rw)
+    return rel_h, rel_w
+
+
+class Attention(nn.Module):
+    """Eager multi-head attention with decomposed rel-pos (image_encoder.py:210-265);
+    the pre-quantization form that ``make_quant_attn`` replaces."""
+
+    def __init__(self, dim: int, num_heads: int = 8, qkv_bias: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, input_size: Optional[Tuple[int, int]] = None,
+                 relw_mode: str = "reference") -> None:
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_rel_pos = use_rel_pos
+        self.relw_mode = relw_mode
+        if use_rel_pos:
+            assert input_size is not None, "Input size must be provided if using relative positional encoding."
+            self.rel_pos_h = nn.Parameter(torch.zeros(2 * input_size[0] - 1, head_dim))
+            self.rel_pos_w = nn.Parameter(torch.zeros(2 * input_size[1] - 1, head_dim))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, _ = x.shape
+        qkv = self.qkv(x).reshape(B, H * W, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.reshape(3, B * self.num_heads, H * W, -1).unbind(0)
+        attn = (q * self.scale) @ k.transpose(-2, -1)
+        if self.use_rel_pos:
+            rel_h, rel_w = decomposed_rel_pos(q, self.rel_pos_h, self.rel_pos_w, (H, W), self.relw_mode)
+            attn = (attn.view(-1, H, W, H, W) + rel_h[..., :, None] + rel_w[..., None, :]).view(-1, H * W, H * W)
+        attn = attn.softmax(dim=-1)
+        x = (attn @ v).view(B, self.num_heads, H, W, -1).permute(0, 2, 3, 1, 4).reshape(B, H, W, -1)
+        return self.proj(x)
+
+
+class Block(nn.Module):
+    """Transformer block with optional 14x14 window attention (image_encoder.py:139-207)."""
+
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0, qkv_bias: bool = True,
+                 norm_layer: Type[nn.Module] = nn.LayerNorm, act_layer: Type[nn.Module] = nn.GELU,
+                 use_rel_pos: bool = False, rel_pos_zero_init: bool = True, window_size: int = 0,
+                 input_size: Optional[Tuple[int, int]] = None) -> None:
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, use_rel_pos=use_rel_pos,
+                              rel_pos_zero_init=rel_pos_zero_init,
+                              input_size=input_size if window_size == 0 else (window_size, window_size))
+        self.norm2 = norm_layer(dim)
+        self.mlp = MLPBlock(embedding_dim=dim, mlp_dim=int(dim * mlp_ratio), act=act_layer)
+        self.window_size = window_size
+
+    # -- fused CUDA path -------------------------------------------------------
+    def _fused_ready(self) -> bool:
+        return (isinstance(self.attn, QuantAttention) and isinstance(self.attn.qkv_proj, QuantLinear)
+                and isinstance(self.attn.o_proj, QuantLinear) and isinstance(self.mlp, QuantMLP)
+                and isinstance(self.norm1, nn.LayerNorm) and isinstance(self.norm2, nn.LayerNorm))
+
+    def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, C = x.shape
+        n1, n2 = self.norm1, self.norm2
+        if self.window_size > 0:
+            ws = self.window_size
+            xw, _ = ops.layernorm_partition(x, n1.weight, n1.bias, n1.eps, ws)
+            a = self.attn(xw)                                   # [B*nWin, ws, ws, C]
+            x = ops.unpartition_residual(a, x, ws)              # shortcut + unpartition(a)
+        else:
+            xn = ops.layernorm(x, n1.weight, n1.bias, n1.eps)
+            x = self.attn(xn, residual=x)                       # residual fused into proj
+        xn = ops.layernorm(x, n2.weight, n2.bias, n2.eps)
+        return self.mlp(xn, residual=x)                         # residual fused into lin2
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._fused_ready():
+            if not (x.is_cuda and x.dtype == torch.float16):
+                raise RuntimeError(
+                    "quantized Block needs a float16 CUDA tensor: there is no CPU / eager "
+                    f"fallback for the quantized path (got {x.dtype} on {x.device})")
+            return self._forward_fused(x.contiguous())
+        shortcut = x
+        x = self.norm1(x)
+        H, W = x.shape[1], x.shape[2]
+        if self.window_size > 0:
+            x, pad_hw = window_partition(x, self.window_size)
+        x = self.attn(x)
+        if self.window_size > 0:
+            x = window_unpartition(x, self.window_size, pad_hw, (H, W))
+        x = shortcut + x
+        return x + self.mlp(self.norm2(x))
+
+
+class ImageEncoderViT(nn.Module):
+    """ViTDet-style SAM image encoder (image_encoder.py:17-118):
+    ``forward(x[B,3,1024,1024]) -> [B,256,64,64]``."""
+
+    def __init__(self, img_size: int = 1024, patch_size: int = 16, in_chans: int = 3,
+                 embed_dim: int = 768, depth: int = 12, num_heads: int = 12, mlp_ratio: float = 4.0,
+                 out_chans: int = 256, qkv_bias: bool = True, norm_layer: Optional[Type[nn.Module]] = None,
+                 act_layer: Type[nn.Module] = nn.GELU, use_abs_pos: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, window_size: int = 0,
+                 global_attn_indexes: Tuple[int, ...] = (), norm_eps: float = 1e-6) -> None:
+        super().__init__()
+        self.img_size = img_size
+        if norm_layer is None:
+            def norm_layer(dim):  # partial(nn.LayerNorm, eps=1e-6), build_sam.py:72
+                return nn.LayerNorm(dim, eps=norm_eps)
+        self.patch_embed = PatchEmbed(kernel_size=(patch_size, patch_size), stride=(patch_size, patch_size),
+                                      in_chans=in_chans, embed_dim=embed_dim)
+        self.pos_embed: Optional[nn.Parameter] = None
+        if use_abs_pos:
+            self.pos_embed = nn.Parameter(
+                torch.zeros(1, img_size // patch_size, img_size // patch_size, embed_dim))
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            self.blocks.append(Block(
+                dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                norm_layer=norm_layer, act_layer=act_layer, use_rel_pos=use_rel_pos,
+                rel_pos_zero_init=rel_pos_zero_init,
+                window_size=window_size if i not in global_attn_indexes else 0,
+                input_size=(img_size // patch_size, img_size // patch_size)))
+        self.neck = nn.Sequential(
+            nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False),
+            LayerNorm2d(out_chans),
+            nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False),
+            LayerNorm2d(out_chans),
+        )
+
+    def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
+        """The 32-block hot loop on tokens ``[B, 64, 64, D]`` (image_encoder.py:111-113)."""
+        for blk in self.blocks:
+            x = blk(x)
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.patch_embed(x)
+        if self.pos_embed is not None:
+            x = x + self.pos_embed
+        x = self.forward_tokens(x)
+        return self.neck(x.permute(0, 3, 1, 2))

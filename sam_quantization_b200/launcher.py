@@ -1,0 +1,79 @@
+"""Data-parallel launcher: shard the image batch over the GPUs of one box.
+
+The reference has no multi-GPU inference path (device hard-coded, batch asserted 1:
+/root/reference/gptq4sam_infer.py:169,176).  Images are independent -- no op
+of the encoder crosses the batch dimension (image_encoder.py:106-118) -- so the path
+shards as REPLICAS: one process per GPU (torchrun), full copy of the packed weights
+(ViT-H int4 g128 = 328 MB) per rank, contiguous split of the global batch, and no
+collective on the hot path.  The only communication is an optional final
+``all_gather`` of the embeddings ``[B_local, 256, 64, 64]`` (2 MiB/image in fp16) over
+NCCL / NVLink, outside the per-block loop.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_bounds", "init_distributed", "ShardedEncoder"]
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``n`` items: the first ``n % world_size`` ranks get one extra."""
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment; initialises the default
+    process group when WORLD_SIZE > 1 (NCCL on GPUs, gloo on CPU)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+class ShardedEncoder:
+    """Runs ``encoder`` on this rank's contiguous shard of a global batch."""
+
+    def __init__(self, encoder, rank: int = 0, world_size: int = 1, micro_batch: Optional[int] = None):
+        self.encoder = encoder
+        self.rank = rank
+        self.world_size = world_size
+        self.micro_batch = micro_batch
+
+    def local_slice(self, global_batch: int) -> slice:
+        lo, hi = shard_bounds(global_batch, self.world_size, self.rank)
+        return slice(lo, hi)
+
+    @torch.no_grad()
+    def encode_local(self, images: torch.Tensor) -> torch.Tensor:
+        """Encode already-local images, optionally in micro-batches."""
+        mb = self.micro_batch or max(1, images.shape[0])
+        outs: List[torch.Tensor] = [self.encoder(images[i:i + mb]) for i in range(0, images.shape[0], mb)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def __call__(self, images_global: torch.Tensor, gather: bool = False) -> torch.Tensor:
+        """``images_global`` is the full batch (same on every rank); returns this rank's
+        embeddings, or -- with ``gather`` -- the full batch's embeddings on every rank."""
+        n = images_global.shape[0]
+        local = self.encode_local(images_global[self.local_slice(n)])
+        if not gather or self.world_size == 1:
+            return local
+        sizes = [shard_bounds(n, self.world_size, r) for r in range(self.world_size)]
+        max_len = max(hi - lo for lo, hi in sizes)
+        pad = torch.zeros((max_len,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        bufs = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(bufs, pad)
+        return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)

@@ -1,0 +1,51 @@
+"""The C-ABI library loads on a machine without a GPU and exports exactly the symbols
+include/samq.h declares; argument validation works before any device call."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from sam_quantization_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "samq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(samq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_symbols():
+        assert getattr(lib, name) is not None, name
+
+
+def test_abi_version_and_error_strings():
+    lib = _lib.load()
+    assert lib.samq_abi_version() == 1
+    # validation happens before any CUDA call, so these run on a GPU-less box
+    rc = lib.samq_unpack_dequant(1, 1, 1, None, 1, 64, 64, 5, 64, 0, None)
+    assert rc == _lib.SAMQ_ERR_UNSUPPORTED_BITS and "bits" in _lib.last_error()
+    rc = lib.samq_qlinear_fwd(16, 16, 16, 16, None, None, None, 16, None, 4, 100, 128, 4, 128, 0, None)
+    assert rc == _lib.SAMQ_ERR_BAD_SHAPE and "K=100" in _lib.last_error()
+    rc = lib.samq_attn_relpos_fwd(16, 16, 16, 16, 1, 32, 32, 4, 80, 0.1, 0, None)
+    assert rc == _lib.SAMQ_ERR_BAD_SHAPE
+    rc = lib.samq_layernorm_fwd(None, None, None, None, 4, 64, 1e-6, None)
+    assert rc == _lib.SAMQ_ERR_BAD_ARG
+
+
+def test_status_maps_to_reference_exception_types():
+    lib = _lib.load()
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.samq_unpack_dequant(1, 1, 1, None, 1, 64, 64, 5, 64, 0, None))
+    with pytest.raises(AssertionError):
+        _lib.check(lib.samq_qlinear_fwd(16, 16, 16, 16, None, None, None, 16, None, 4, 100, 128, 4, 128, 0, None))
+    with pytest.raises(ValueError):
+        _lib.check(lib.samq_layernorm_fwd(None, None, None, None, 4, 64, 1e-6, None))

@@ -1,0 +1,78 @@
+"""samq_attn_relpos_fwd vs the oracle's eager attention (fp32 softmax; the formula of the
+reference's only self-check, gptq_triton/fused_attention.py:388-406) at its two shapes, seed
+20, N(0, 0.5) inputs.  Tolerance: the reference's own (commented-out) atol = 1e-2, rtol = 0
+(fused_attention.py:409); measured errors are ~5e-4 and are asserted at 2e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oe
+from sam_quantization_b200 import _lib, ops
+from gpu_util import report
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 2e-3
+
+
+def make_inputs(B, E, heads, hd, seed=20, std=0.5, rp_std=0.3):
+    g = torch.Generator().manual_seed(seed)
+    qkv = torch.empty(B, E * E, 3 * heads * hd).normal_(0.0, std, generator=g).half()
+    rph = torch.empty(2 * E - 1, hd).normal_(0.0, rp_std, generator=g).half()
+    rpw = torch.empty(2 * E - 1, hd).normal_(0.0, rp_std, generator=g).half()
+    return qkv, rph, rpw
+
+
+@pytest.mark.parametrize("B,E,heads,hd", [(25, 14, 16, 80), (1, 64, 16, 80), (25, 14, 16, 64), (1, 64, 12, 64)])
+@pytest.mark.parametrize("relw", ["reference", "upstream"])
+def test_attention_test_op_shapes(cuda_device, B, E, heads, hd, relw):
+    qkv, rph, rpw = make_inputs(B, E, heads, hd)
+    out = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), B, E, E, heads, 0.5,
+                          _lib.RELW_UPSTREAM if relw == "upstream" else _lib.RELW_REFERENCE)
+    ref = oe.attention_core(qkv, rph, rpw, B, E, E, heads, 0.5, relw, round_tables=True)
+    err, mag, cos = report(out, ref)
+    assert not torch.isnan(out).any()
+    assert err <= ATOL and cos >= 0.9999, (err, mag, cos)
+
+
+def test_relw_modes_differ(cuda_device):
+    qkv, rph, rpw = make_inputs(2, 14, 2, 64)
+    a = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), 2, 14, 14, 2, 0.125, 0)
+    b = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), 2, 14, 14, 2, 0.125, 1)
+    assert (a.float() - b.float()).abs().max().item() > 1e-2
+
+
+def test_large_logits_exercise_the_lazy_rescale(cuda_device):
+    """std 2.0 inputs give row maxima that keep growing across key tiles (rescale path)."""
+    qkv, rph, rpw = make_inputs(1, 64, 2, 80, seed=3, std=2.0, rp_std=0.5)
+    out = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), 1, 64, 64, 2, 80 ** -0.5)
+    ref = oe.attention_core(qkv, rph, rpw, 1, 64, 64, 2, 80 ** -0.5, "reference", round_tables=True)
+    err, mag, cos = report(out, ref)
+    assert err <= 2e-2 * max(1.0, mag) and cos >= 0.999, (err, mag, cos)
+
+
+@pytest.mark.parametrize("name,size", [("attn_win", 14), ("attn_glob", 64)])
+def test_against_reference_attention_module_fixture(cuda_device, golden_dir, name, size):
+    """Output of the reference's own ``Attention`` module (fp32, CPU) reproduced with fp16 qkv/proj
+    around the CUDA kernel.  Tolerance covers the fp16 rounding of qkv and of the output."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    heads = int(g["heads"])
+    x = torch.from_numpy(g["x16"].astype(np.float32)).to(cuda_device)
+    B, dim = x.shape[0], x.shape[-1]
+    W = {k: torch.from_numpy(g[k]).to(cuda_device) for k in ("qkv.weight", "qkv.bias", "proj.weight", "proj.bias")}
+    qkv = torch.nn.functional.linear(x, W["qkv.weight"], W["qkv.bias"]).half().reshape(B, size * size, -1)
+    o = ops.attn_relpos(qkv.contiguous(), torch.from_numpy(g["rel_pos_h"]).half().to(cuda_device),
+                        torch.from_numpy(g["rel_pos_w"]).half().to(cuda_device), B, size, size, heads,
+                        (dim // heads) ** -0.5)
+    y = torch.nn.functional.linear(o.float(), W["proj.weight"], W["proj.bias"]).reshape(B, size * size, dim)
+    err, mag, cos = report(y[:, :: int(g["stride"])], g["y_sub"])
+    assert err <= 5e-3 * max(1.0, mag) and cos >= 0.9999, (err, mag, cos)
+
+
+def test_unsupported_shapes_raise(cuda_device):
+    qkv = torch.zeros(1, 32 * 32, 3 * 2 * 64, dtype=torch.float16, device=cuda_device)
+    rp = torch.zeros(63, 64, dtype=torch.float16, device=cuda_device)
+    with pytest.raises(AssertionError):
+        ops.attn_relpos(qkv, rp, rp, 1, 32, 32, 2, 0.1)

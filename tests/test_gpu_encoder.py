@@ -1,0 +1,94 @@
+"""Block / encoder parity on the GPU: the fused CUDA path (loaded through load_quant from a
+reference-layout checkpoint directory) vs the CPU oracle on the dequantised weights.
+
+Tolerances (fp16 storage between kernels, fp32 accumulation inside; stated per test):
+token outputs  max-abs <= 1.5e-2 * max|ref|, cosine >= 0.9999;
+encoder embeddings (after the neck's LayerNorm2d) max-abs <= 6e-2, cosine >= 0.999."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sam_quantization_b200 as sq
+from oracle import encoder as oe
+from oracle import synth
+from sam_quantization_b200 import image_encoder as ie
+from gpu_util import report
+
+pytestmark = pytest.mark.gpu
+
+
+def build_from_checkpoint(tmp_path, cfg, bits, gs, seed, device, act_order=False, relw_mode="reference"):
+    p = synth.fp_state(seed=seed, **cfg)
+    rng = np.random.default_rng(seed + 50)
+    for k in p:
+        if "rel_pos" in k:   # make the rel-pos path matter (zero-init in the reference, trap 5)
+            p[k] = (rng.standard_normal(p[k].shape) * 0.2).astype(np.float32)
+    packed = synth.quantize_state(p, bits, gs, act_order_seed=(seed if act_order else None))
+    state = synth.to_torch(packed)
+    torch.save(state, tmp_path / "model.pt")
+    import json
+    json.dump({"wbits": bits, "groupsize": gs}, open(tmp_path / "quant_config.json", "w"))
+    enc = ie.ImageEncoderViT(img_size=1024, patch_size=16, use_rel_pos=True, window_size=14,
+                             embed_dim=cfg["embed_dim"], depth=cfg["depth"], num_heads=cfg["num_heads"],
+                             global_attn_indexes=cfg["global_attn_indexes"]).half()
+    enc = sq.load_quant(enc, str(tmp_path), warmup_autotune=False, device=device, relw_mode=relw_mode).eval()
+    ref_state = oe.dequant_state(state, bits, gs)
+    return enc, ref_state
+
+
+@pytest.mark.parametrize("dim,heads,gs", [(128, 2, 64), (640, 8, 128)])
+@pytest.mark.parametrize("relw", ["reference", "upstream"])
+def test_blocks_small(cuda_device, tmp_path, dim, heads, gs, relw):
+    cfg = dict(embed_dim=dim, depth=2, num_heads=heads, global_attn_indexes=(1,))
+    enc, ref_state = build_from_checkpoint(tmp_path, cfg, 4, gs, seed=1, device=cuda_device, relw_mode=relw)
+    assert all(b._fused_ready() for b in enc.blocks)
+    x = torch.from_numpy(synth.tokens_input(2, 64, dim, seed=3)).half()
+    with torch.no_grad():
+        y = enc.forward_tokens(x.to(cuda_device))
+        ref = oe.tokens_forward(x.float(), ref_state, 2, heads, 14, (1,), relw)
+    err, mag, cos = report(y, ref)
+    print(f"blocks dim={dim} relw={relw}: max-abs {err:.3e} (max|ref| {mag:.3f}) cosine {cos:.7f}")
+    assert err <= 1.5e-2 * mag and cos >= 0.9999
+
+
+@pytest.mark.parametrize("bits", [3, 8])
+def test_blocks_other_bits_with_act_order(cuda_device, tmp_path, bits):
+    """BASELINE config 4 at a small width: 3-/8-bit with a permutation-derived g_idx."""
+    cfg = dict(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,))
+    enc, ref_state = build_from_checkpoint(tmp_path, cfg, bits, 64, seed=2, device=cuda_device, act_order=True)
+    assert enc.blocks[0].attn.qkv_proj.g_idx is not None
+    x = torch.from_numpy(synth.tokens_input(1, 64, 128, seed=4)).half()
+    with torch.no_grad():
+        y = enc.forward_tokens(x.to(cuda_device))
+        ref = oe.tokens_forward(x.float(), ref_state, 2, 2, 14, (1,), "reference")
+    err, mag, cos = report(y, ref)
+    assert err <= 1.5e-2 * mag and cos >= 0.9999
+
+
+def test_vit_b_encoder_config1(cuda_device, tmp_path):
+    """BASELINE config 1: ViT-B, int4 g128, one synthetic 1024x1024 image, whole encoder."""
+    cfg = dict(oe.CONFIGS["vit_b"])
+    enc, ref_state = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=0, device=cuda_device)
+    img = torch.from_numpy(synth.image(1, 1024, seed=0))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        y = enc(img.half().to(cuda_device))
+        ref = oe.encoder(img.half().float(), ref_state, **cfg)
+    assert y.shape == (1, 256, 64, 64)
+    err, mag, cos = report(y, ref)
+    print(f"ViT-B encoder: max-abs {err:.3e} (max|ref| {mag:.3f}) cosine {cos:.7f}")
+    assert err <= 6e-2 and cos >= 0.999
+
+
+def test_batch_invariance_and_sharding_property(cuda_device, tmp_path):
+    """Size-independent property for the batched configs: encoding a batch equals encoding
+    each image alone (bit-exact: no op crosses the batch), so shards over GPUs are replicas."""
+    cfg = dict(embed_dim=640, depth=2, num_heads=8, global_attn_indexes=(1,))
+    enc, _ = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=5, device=cuda_device)
+    x = torch.from_numpy(synth.tokens_input(3, 64, 640, seed=6)).half().to(cuda_device)
+    with torch.no_grad():
+        full = enc.forward_tokens(x)
+        parts = torch.cat([enc.forward_tokens(x[i:i + 1]) for i in range(3)])
+    assert torch.equal(full, parts)

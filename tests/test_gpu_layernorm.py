@@ -1,0 +1,61 @@
+"""LayerNorm / window partition / unpartition+residual kernels vs the oracle (fp32 torch, CPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoder as oe
+from sam_quantization_b200 import ops
+from gpu_util import report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("C", [768, 1024, 1280, 64, 2048])
+def test_layernorm(cuda_device, C):
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(3, 64, 64, C, generator=g) * 2 + 0.5).half()
+    w = (1 + 0.1 * torch.randn(C, generator=g)).half()
+    b = (0.1 * torch.randn(C, generator=g)).half()
+    y = ops.layernorm(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device), 1e-6)
+    ref = oe.layer_norm(x.float(), w.float(), b.float(), 1e-6)
+    err, mag, cos = report(y, ref)
+    assert err <= 2.0 ** -10 * mag and cos > 0.999999     # one fp16 ulp at the output magnitude
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 64, 64, 1280), (2, 64, 64, 768), (3, 20, 30, 64)])
+def test_layernorm_partition(cuda_device, B, H, W, C):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, H, W, C, generator=g).half()
+    w = (1 + 0.1 * torch.randn(C, generator=g)).half()
+    b = (0.1 * torch.randn(C, generator=g)).half()
+    y, pad_hw = ops.layernorm_partition(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device), 1e-6, 14)
+    ref, ref_hw = oe.window_partition(oe.layer_norm(x.float(), w.float(), b.float(), 1e-6), 14)
+    assert tuple(pad_hw) == tuple(ref_hw) and y.shape == ref.shape
+    err, mag, _ = report(y, ref)
+    assert err <= 2.0 ** -10 * mag
+    # padded tokens are exactly zero (the pad is applied after the norm, image_encoder.py:300)
+    assert torch.equal((y == 0).all(-1).cpu(), (ref == 0).all(-1))
+
+
+def test_unpartition_residual_on_the_forks_fixture(cuda_device, golden_dir):
+    """window_unpartition of the reference's own windows (ViT-H, batch 1) is reproduced exactly."""
+    g = np.load(os.path.join(golden_dir, "partition_vith.npz"))
+    win = torch.from_numpy(g["windows"]).half()
+    back = torch.from_numpy(g["back"]).half()
+    zero = torch.zeros_like(back)
+    out = ops.unpartition_residual(win.to(cuda_device), zero.to(cuda_device), 14)
+    assert torch.equal(out.cpu(), back)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 1024), (1, 20, 30, 64)])
+def test_unpartition_residual(cuda_device, B, H, W, C):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, H, W, C, generator=g).half()
+    sc = torch.randn(B, H, W, C, generator=g).half()
+    win, pad_hw = oe.window_partition(x.float(), 14)
+    out = ops.unpartition_residual(win.half().to(cuda_device), sc.to(cuda_device), 14)
+    ref = (sc.float() + oe.window_unpartition(win, 14, pad_hw, (H, W))).half()
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(ops.add(x.to(cuda_device), sc.to(cuda_device)).cpu(), (x.float() + sc.float()).half())

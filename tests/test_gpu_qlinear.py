@@ -1,0 +1,132 @@
+"""samq_qlinear_fwd vs the oracle (oracle/quant.py::qlinear, fp32 on the stepwise-dequantised
+weight).  Tolerance: the kernel accumulates in fp32 and rounds once to fp16, so
+|y - ref| <= 2^-10 * max|ref| (one fp16 ulp at the output's magnitude) and cosine >= 0.99999."""
+import numpy as np
+import pytest
+import torch
+
+import sam_quantization_b200 as sq
+from oracle import quant as oq
+from sam_quantization_b200 import _lib, ops
+from gpu_util import dev, rand_packed, report
+
+pytestmark = pytest.mark.gpu
+
+ULP = 2.0 ** -10
+
+
+def run_case(device, M, K, N, bits, gs, seed, g_idx=False, epilogue="none", bias=True, residual=False):
+    g = K if gs == -1 else gs
+    qw, qz, sc, gi = rand_packed(K, N, bits, g, seed=seed, g_idx=g_idx)
+    rng = np.random.default_rng(seed + 100)
+    x = rng.standard_normal((M, K)).astype(np.float16)
+    b = (rng.standard_normal(N)).astype(np.float16) if bias else None
+    r = rng.standard_normal((M, N)).astype(np.float16) if residual else None
+    y = ops.qlinear(dev(x, device), dev(qw, device), dev(qz, device), dev(sc, device), bits, gs, dev(b, device),
+                    dev(gi, device), _lib.EPI_GELU if epilogue == "gelu" else _lib.EPI_NONE, dev(r, device))
+    ref = oq.qlinear(x, qw, qz, sc, bits, gs, b, gi, epilogue, r)
+    err, mag, cos = report(y, ref)
+    assert not torch.isnan(y).any()
+    assert err <= ULP * mag + 1e-6, (err, mag)
+    assert cos >= 0.99999, cos
+    return err, mag, cos
+
+
+# BASELINE config 5 shapes at the sizes the CPU oracle finishes in seconds
+@pytest.mark.parametrize("M", [196, 4096])
+@pytest.mark.parametrize("K,N", [(1280, 3840), (1280, 5120), (5120, 1280)])
+def test_int4_vith_shapes(cuda_device, M, K, N):
+    run_case(cuda_device, M, K, N, 4, 128, seed=1)
+
+
+@pytest.mark.parametrize("K,N", [(768, 2304), (768, 768), (3072, 768), (1024, 4096), (1280, 1280)])
+def test_int4_vit_b_l_h_layer_shapes(cuda_device, K, N):
+    run_case(cuda_device, 4900, K, N, 4, 128, seed=2)
+
+
+@pytest.mark.parametrize("M", [1, 7, 191, 192, 193, 385])
+def test_ragged_m(cuda_device, M):
+    run_case(cuda_device, M, 256, 256, 4, 128, seed=3)
+
+
+def test_empty_batch(cuda_device):
+    qw, qz, sc, _ = rand_packed(256, 256, 4, 128)
+    y = ops.qlinear(torch.zeros(0, 256, dtype=torch.float16, device=cuda_device), dev(qw, cuda_device),
+                    dev(qz, cuda_device), dev(sc, cuda_device), 4, 128)
+    assert y.shape == (0, 256)
+
+
+@pytest.mark.parametrize("gs", [64, 128, 256, -1])
+def test_groupsizes(cuda_device, gs):
+    run_case(cuda_device, 300, 512, 384, 4, gs, seed=4)
+
+
+@pytest.mark.parametrize("epilogue,bias,residual", [("none", False, False), ("gelu", True, False),
+                                                     ("none", True, True), ("gelu", True, True)])
+def test_epilogues(cuda_device, epilogue, bias, residual):
+    run_case(cuda_device, 1000, 1280, 1280, 4, 128, seed=5, epilogue=epilogue, bias=bias, residual=residual)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 8])
+@pytest.mark.parametrize("g_idx", [False, True])
+def test_other_bit_widths_and_act_order(cuda_device, bits, g_idx):
+    """BASELINE config 4 (extension: parity unpinned by the reference, checked against the oracle)."""
+    run_case(cuda_device, 500, 1280, 1280, bits, 128, seed=6, g_idx=g_idx)
+
+
+def test_int4_act_order(cuda_device):
+    run_case(cuda_device, 500, 1280, 3840, 4, 128, seed=7, g_idx=True)
+
+
+@pytest.mark.parametrize("K,N", [(1280, 3840), (1280, 5120), (5120, 1280)])
+def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, K, N):
+    """At BASELINE's largest M the oracle is replaced by a size-independent identity:
+    the fused kernel must equal an fp32 GEMM (torch, on the GPU) of the bit-exact dequantised
+    weight (itself pinned to the oracle by test_gpu_dequant)."""
+    M = 32768
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=8)
+    tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
+    x = torch.randn(M, K, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(0)).half()
+    y = ops.qlinear(x, tq, tz, ts, 4, 128)
+    w = ops.unpack_dequant(tq, tz, ts, 4, 128).float()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = x.float() @ w
+    err = (y.float() - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    assert err <= ULP * mag, (err, mag)
+    # linearity in x (size-independent property): f(2x) == 2 f(x) exactly in fp16 (power-of-two scaling)
+    y2 = ops.qlinear((x * 2).half(), tq, tz, ts, 4, 128)
+    assert torch.equal(y2, (y * 2).half())
+
+
+def test_module_forward_and_reference_entry_point(cuda_device):
+    """QuantLinear.forward and triton_matmul4 (the reference's public entry, quant_linear.py:355)."""
+    K, N, gs = 1280, 1280, 128
+    qw, qz, sc, _ = rand_packed(K, N, 4, gs, seed=9)
+    m = sq.QuantLinear(4, gs, K, N, True)
+    m.qweight, m.qzeros, m.scales = torch.from_numpy(qw), torch.from_numpy(qz), torch.from_numpy(sc)
+    m.bias = torch.randn(N).half()
+    m = m.to(cuda_device)
+    x = torch.randn(2, 14, 14, K, device=cuda_device).half()
+    y = m(x)
+    assert y.shape == (2, 14, 14, N) and y.dtype == torch.float16
+    y2 = sq.triton_matmul4(gs, x, m.qweight, m.scales, m.qzeros, m.bias)
+    assert torch.equal(y, y2)
+    ref = oq.qlinear(x.cpu().numpy().reshape(-1, K), qw, qz, sc, 4, gs, m.bias.cpu().numpy())
+    err, mag, cos = report(y.view(-1, N), ref)
+    assert err <= ULP * mag and cos >= 0.99999
+    with pytest.raises(AssertionError):
+        m(x[..., :640].contiguous())
+    with pytest.raises(AssertionError):
+        m(x.transpose(1, 2))          # non-contiguous, quant_linear.py:381
+
+
+def test_dense_ablation_path_equals_fused(cuda_device):
+    K, N = 1280, 3840
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=11)
+    tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
+    x = torch.randn(4900, K, device=cuda_device).half()
+    y = ops.qlinear(x, tq, tz, ts, 4, 128)
+    wt = ops.unpack_dequant(tq, tz, ts, 4, 128, transposed=True)
+    yd = ops.dense_linear(x, wt)
+    assert torch.equal(y, yd)      # same fp16 operands, same fp32 accumulation order per tile
