@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the GPTQ-int4 SAM image-encoder hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model vit_h] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...       # the reference's CPU dequant path (oracle port)
+
+One step = one pass of the whole quantized encoder (patch embed, 32 blocks, neck) over one
+batch of ``--batch`` synthetic 1024x1024 images per GPU (weak scaling: replicas, no collective
+on the data path).  Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# algorithmic GFLOP per 1024x1024 image (2MKN per GEMM, windowed blocks on
+# 4900 padded tokens as the reference executes them; 4 S^2 hd per head for attention)
+GFLOP_PER_IMAGE = {"vit_b": 972.1, "vit_l": 2985.7, "vit_h": 5961.1}
+LINEAR_GFLOP_PER_IMAGE = {"vit_b": 726.1, "vit_l": 2608.8, "vit_h": 5449.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), tflops=d.get("bf16_tflops", 1590.0),
+                    tflops_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline = the oracle port of the reference's PyTorch dequant path
+# --------------------------------------------------------------------------------------
+def cpu_reference_prepare(model_name: str, packed_state, n_blocks: int):
+    """Oracle-dequantised fp32 weights of the stem, the first ``n_blocks`` blocks and the neck."""
+    from oracle import encoder as oe
+
+    sub = {k: v for k, v in packed_state.items()
+           if not k.startswith("blocks.") or int(k.split(".")[1]) < n_blocks}
+    return oe.dequant_state(sub, 4, 128)
+
+
+def cpu_reference_images_per_s(model_name: str, p, n_blocks: int):
+    """Time ``n_blocks`` consecutive blocks (from block 0: for ViT-H the first 8 blocks have the
+    full model's 7:1 windowed:global mix) + stem + neck of ONE image on the host cores with the
+    oracle, and extrapolate the block time to the full depth.
+    Returns (images/s, seconds per image, cores)."""
+    from oracle import encoder as oe
+    from oracle import synth
+
+    cfg = oe.CONFIGS[model_name]
+    depth = cfg["depth"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img = torch.from_numpy(synth.image(1, 1024, seed=0)).half().float()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        x = torch.nn.functional.conv2d(img, p["patch_embed.proj.weight"], p["patch_embed.proj.bias"], stride=16)
+        x = x.permute(0, 2, 3, 1) + p["pos_embed"]
+        t1 = time.perf_counter()
+        x = oe.tokens_forward(x, p, n_blocks, cfg["num_heads"], 14, cfg["global_attn_indexes"])
+        t2 = time.perf_counter()
+        y = x.permute(0, 3, 1, 2)
+        y = torch.nn.functional.conv2d(y, p["neck.0.weight"])
+        y = oe._layer_norm_2d(y, p["neck.1.weight"], p["neck.1.bias"])
+        y = torch.nn.functional.conv2d(y, p["neck.2.weight"], padding=1)
+        y = oe._layer_norm_2d(y, p["neck.3.weight"], p["neck.3.bias"])
+        t3 = time.perf_counter()
+    sec = (t1 - t0) + (t3 - t2) + (t2 - t1) * depth / n_blocks
+    return 1.0 / sec, sec, cores
+
+
+def packed_state_cpu(enc):
+    """Reference-layout state (``...attn.qkv.qweight`` etc.) of a fused encoder, on the CPU."""
+    out = {}
+    for k, v in enc.state_dict().items():
+        k = k.replace(".attn.qkv_proj.", ".attn.qkv.").replace(".attn.o_proj.", ".attn.proj.")
+        out[k] = v.detach().cpu()
+    return out
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--model", default="vit_h", choices=sorted(GFLOP_PER_IMAGE))
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = f"SAM {args.model.replace('_', '-').upper().replace('VIT', 'ViT')} GPTQ-int4 encoder images/s"
+    config = {"workload": f"SAM {args.model} image encoder, GPTQ int4 groupsize 128, random-init packed weights, "
+                          f"synthetic 1024x1024 images, batch {args.batch}/GPU/step",
+              "global_batch": args.batch * world, "parallelism": f"dp{world} (replicas, no data-path collective)",
+              "l2": "no explicit flush: the working set of one step (packed weights + activations of the batch, "
+                    ">1 GB at batch 8) exceeds the 126 MB L2; input batches rotate over 3 buffers"}
+
+    from sam_quantization_b200.synthetic import random_quantized_encoder
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        enc = random_quantized_encoder(args.model, 4, 128, seed=0, device="cpu")
+        state = packed_state_cpu(enc)
+        del enc
+        # size the per-step sample so the whole run ends within a few minutes
+        p1 = cpu_reference_prepare(args.model, state, 1)
+        t0 = time.perf_counter()
+        cpu_reference_images_per_s(args.model, p1, 1)
+        per_block = time.perf_counter() - t0
+        budget = 150.0 / max(1, args.steps + args.warmup)
+        depth = len({k.split(".")[1] for k in state if k.startswith("blocks.")})
+        n_blocks = next((n for n in (8, 4, 2) if n <= depth and per_block * n <= budget), 1)
+        p = cpu_reference_prepare(args.model, state, n_blocks)
+        cores = os.cpu_count() or 1
+        for _ in range(args.warmup):
+            cpu_reference_images_per_s(args.model, p, n_blocks)
+        t0 = time.perf_counter()
+        secs = [cpu_reference_images_per_s(args.model, p, n_blocks)[1] for _ in range(args.steps)]
+        wall = time.perf_counter() - t0
+        sec = statistics.mean(secs)
+        value = 1.0 / sec
+        sample = (f"per step: 1 image through stem + first {n_blocks} of {depth} blocks + neck, fp32 torch on all host "
+                  f"cores with the oracle's dequantised weights; block time extrapolated to the full depth")
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": wall}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch.distributed as dist
+
+    from sam_quantization_b200 import _lib, ops
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+    _lib.device_check(dev)
+    torch.backends.cudnn.benchmark = True
+
+    enc = random_quantized_encoder(args.model, 4, 128, seed=0, device=dev)
+    B = args.batch
+    nbuf = 3
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    inputs = [torch.randn(B, 3, 1024, 1024, device=dev, generator=gen).half() for _ in range(nbuf)]
+    host_in = [t.cpu().pin_memory() for t in inputs]
+    host_out = torch.empty(B, 256, 64, 64, dtype=torch.float16).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            enc(inputs[i % nbuf])
+        barrier()
+
+        # ---- timed region: device-resident inputs -------------------------------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            out = enc(inputs[i % nbuf])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end-to-end: host buffers, H2D + encoder + D2H per step ----------------------
+        for i in range(2):
+            host_out.copy_(enc(host_in[i % nbuf].to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(args.steps):
+            x = host_in[i % nbuf].to(dev, non_blocking=True)
+            host_out.copy_(enc(x), non_blocking=True)
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+
+        # ---- roofline of the dominant kernel (dequant-GEMM), instrumented replay ------------
+        gemm_ms, gemm_flops, gemm_calls = 0.0, 0.0, 0
+        rec = []
+        orig = ops.qlinear
+
+        def timed_qlinear(x, qweight, *a, **kw):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            y = orig(x, qweight, *a, **kw)
+            t.record()
+            rec.append((s, t, 2.0 * (x.numel() // x.shape[-1]) * x.shape[-1] * qweight.shape[1]))
+            return y
+
+        ops.qlinear = timed_qlinear
+        import sam_quantization_b200.quant_linear as ql
+        ql.ops.qlinear = timed_qlinear
+        for i in range(2):
+            enc(inputs[i % nbuf])
+        torch.cuda.synchronize()
+        ops.qlinear = orig
+        for s, t, fl in rec:
+            gemm_ms += s.elapsed_time(t)
+            gemm_flops += fl
+            gemm_calls += 1
+
+    t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t_ms.tolist()
+
+    if rank == 0:
+        peaks = load_peaks()
+        images = args.steps * B * world
+        value = images / (ms / 1e3)
+        e2e_value = images / (ms_e2e / 1e3)
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "qlinear_traffic.json")
+        if os.path.exists(prof):
+            with open(prof) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        line = {
+            "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (int4 weights dequantised to fp16)",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 1024 * 1024 * 2,
+                    "d2h_bytes_per_step": B * 256 * 64 * 64 * 2},
+            "roofline": {
+                "kernel": "qlinear_kernel<192, fused int4> (dequant-GEMM, all 4 linears of every block)",
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": (achieved / peaks["tflops_sustained"]) if achieved else None,
+                "frac_of_burst_peak": (achieved / peaks["tflops"]) if achieved else None,
+                "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['tflops']})",
+                "traffic": traffic,
+                "how": f"CUDA events around each of the {gemm_calls} GEMM launches of 2 instrumented steps run right "
+                       f"after the timed region; algorithmic 2*M*K*N per launch",
+                "share_of_step": (gemm_ms / 2) / (ms / args.steps) if gemm_ms > 0 else None,
+            },
+            "model_tflops": value * GFLOP_PER_IMAGE[args.model] / 1e3,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                nb = 8
+                pcpu = cpu_reference_prepare(args.model, packed_state_cpu(enc), nb)
+                ips, sec, cores = cpu_reference_images_per_s(args.model, pcpu, nb)
+                line["cpu_baseline"] = {
+                    "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                    "sample": "1 image: stem + first 8 blocks (7 windowed + 1 global) + neck in fp32 torch on the "
+                              "host with the oracle's dequantised weights, block time extrapolated to full depth"}
+            except Exception as ex:  # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {ex!r}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

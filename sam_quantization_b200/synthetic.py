@@ -30,11 +30,29 @@ def randomize_packed_(model: nn.Module, seed: int = 0, scale_lo: float = 0.003, 
             p.copy_(torch.randn(p.shape, generator=g) * 0.02)   # zero-init in the reference (trap 5)
 
 
+@torch.no_grad()
+def _materialize_meta_(model: nn.Module, seed: int) -> None:
+    """Give real storage + a ViT-style init to every parameter still on the meta device
+    (LayerNorm -> 1/0, everything else ~ N(0, 0.02))."""
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in model.modules():
+        for pname, p in list(mod.named_parameters(recurse=False)):
+            if not p.is_meta:
+                continue
+            if isinstance(mod, nn.LayerNorm) or type(mod).__name__ == "LayerNorm2d":
+                val = torch.ones(p.shape) if pname == "weight" else torch.zeros(p.shape)
+            else:
+                val = torch.randn(p.shape, generator=g) * 0.02
+            setattr(mod, pname, nn.Parameter(val, requires_grad=False))
+
+
 def random_quantized_encoder(name: str = "vit_h", bits: int = 4, groupsize: int = 128, seed: int = 0,
                              device: str = "cuda", relw_mode: str = "reference", **overrides) -> ImageEncoderViT:
     torch.manual_seed(seed)
-    enc = build_image_encoder(name, **overrides)
+    with torch.device("meta"):          # skip the 2.5 GB fp32 init of Linear weights that get replaced
+        enc = build_image_encoder(name, **overrides)
     make_quant(enc, bits, groupsize)
+    _materialize_meta_(enc, seed)
     randomize_packed_(enc, seed)
     enc = enc.half()
     make_quant_attn(enc, relw_mode=relw_mode)

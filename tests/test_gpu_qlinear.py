@@ -94,9 +94,13 @@ def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, K, N):
     err = (y.float() - ref).abs().max().item()
     mag = ref.abs().max().item()
     assert err <= ULP * mag, (err, mag)
-    # linearity in x (size-independent property): f(2x) == 2 f(x) exactly in fp16 (power-of-two scaling)
+    # linearity in x (size-independent property): f(2x) == 2 f(x) exactly in fp16 (power-of-two
+    # scaling commutes with every rounding) wherever the output is a normal fp16 number;
+    # subnormal outputs may differ by one subnormal step (2^-24)
     y2 = ops.qlinear((x * 2).half(), tq, tz, ts, 4, 128)
-    assert torch.equal(y2, (y * 2).half())
+    normal = y.abs() >= 2.0 ** -13
+    assert torch.equal(y2[normal], (y * 2).half()[normal])
+    assert (y2.float() - 2 * y.float()).abs().max().item() <= 2.0 ** -23
 
 
 def test_module_forward_and_reference_entry_point(cuda_device):
