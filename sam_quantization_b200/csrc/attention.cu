@@ -168,7 +168,8 @@ attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // whole warp runs the loop convergently (uniform registers), one elected lane issues
+    {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0);
       constexpr uint32_t idesc_t = make_idesc_f16(128, C::kRpRows, 0);
       constexpr uint32_t idesc_pv_main = make_idesc_f16(128, 64, 1);
@@ -178,28 +179,28 @@ attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
 
       // S_buf = Q . B^T for a K-major B tile (K tile or rel-pos table)
       auto mma_q_times = [&](uint32_t d_tmem, const uint8_t* b_main_ptr, const uint8_t* b_tail_ptr,
-                             uint32_t idesc) {
+                             uint32_t idesc, uint64_t* done_bar) {
         const uint64_t b_main = make_smem_desc(smem_u32(b_main_ptr), 0, 1024, kLayoutSw128);
+        const uint64_t b_tail = make_smem_desc(smem_u32(b_tail_ptr), 0, 256, kLayoutSw32);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc, k > 0);
-        if (C::kTail) {
-          const uint64_t b_tail = make_smem_desc(smem_u32(b_tail_ptr), 0, 256, kLayoutSw32);
-          tc_mma_ss(d_tmem, q_tail, b_tail, idesc, 1);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc, k > 0);
+          if (C::kTail) tc_mma_ss(d_tmem, q_tail, b_tail, idesc, 1);
+          if (done_bar) tc_commit(done_bar);
         }
+        __syncwarp();
       };
 
       mbar_wait(q_full, 0);
       tc_fence_after();
-      mma_q_times(tmem_base + C::cS0, sRph, sRph + C::kRpMainBytes, idesc_t);
-      mma_q_times(tmem_base + C::cS1, sRpw, sRpw + C::kRpMainBytes, idesc_t);
-      tc_commit(t_full);
+      mma_q_times(tmem_base + C::cS0, sRph, sRph + C::kRpMainBytes, idesc_t, nullptr);
+      mma_q_times(tmem_base + C::cS1, sRpw, sRpw + C::kRpMainBytes, idesc_t, t_full);
 
       mbar_wait(&kv_full[0], 0);
       mbar_wait(t_done, 0);  // softmax threads have copied T_h / T_w out of the S buffers
       tc_fence_after();
-      mma_q_times(tmem_base + C::cS0, sKV, sKV + C::kMainBytes, idesc_qk);
-      tc_commit(&s_full[0]);
+      mma_q_times(tmem_base + C::cS0, sKV, sKV + C::kMainBytes, idesc_qk, &s_full[0]);
 
       int s = 0;
       uint32_t ph = 0;
@@ -212,8 +213,8 @@ attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
           tc_fence_after();
           const uint8_t* sK1 = sKV + s1 * 2 * C::kTileBytes;
           // in-order tensor pipe: this overwrite of S[(j+1)&1] is ordered after PV(j-1)
-          mma_q_times(tmem_base + (((j + 1) & 1) ? C::cS1 : C::cS0), sK1, sK1 + C::kMainBytes, idesc_qk);
-          tc_commit(&s_full[(j + 1) & 1]);
+          mma_q_times(tmem_base + (((j + 1) & 1) ? C::cS1 : C::cS0), sK1, sK1 + C::kMainBytes, idesc_qk,
+                      &s_full[(j + 1) & 1]);
         }
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
@@ -221,18 +222,19 @@ attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
         const uint32_t p_tmem = tmem_base + ((j & 1) ? C::cS1 : C::cS0);
         const int keys = (S - j * 128) < 128 ? (S - j * 128) : 128;
         const int ksteps = (keys + 15) / 16;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          const uint64_t v_main = make_smem_desc(smem_u32(sV + ks * 2048), C::kMainBytes, 1024, kLayoutSw128);
-          tc_mma_ts(tmem_base + C::cO, p_tmem + ks * 8, v_main, idesc_pv_main, acc);
-          if (C::kTail) {
-            const uint64_t v_tail =
-                make_smem_desc(smem_u32(sV + C::kMainBytes + ks * 512), C::kTailBytes, 256, kLayoutSw32);
-            tc_mma_ts(tmem_base + C::cO + 64, p_tmem + ks * 8, v_tail, idesc_pv_tail, acc);
+        const uint64_t v_main0 = make_smem_desc(smem_u32(sV), C::kMainBytes, 1024, kLayoutSw128);
+        const uint64_t v_tail0 = make_smem_desc(smem_u32(sV + C::kMainBytes), C::kTailBytes, 256, kLayoutSw32);
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+            tc_mma_ts(tmem_base + C::cO, p_tmem + ks * 8, v_main0 + (ks * 2048 >> 4), idesc_pv_main, acc);
+            if (C::kTail)
+              tc_mma_ts(tmem_base + C::cO + 64, p_tmem + ks * 8, v_tail0 + (ks * 512 >> 4), idesc_pv_tail, acc);
           }
+          tc_commit(&kv_empty[s]);
+          tc_commit(&pv_done[j & 1]);
         }
-        tc_commit(&kv_empty[s]);
-        tc_commit(&pv_done[j & 1]);
+        __syncwarp();
         if (++s == C::kStages) { s = 0; ph ^= 1; }
       }
     }

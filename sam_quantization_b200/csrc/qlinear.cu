@@ -14,13 +14,12 @@
 // zero are thread-constant inside a quantisation group and the packed words
 // qweight[k/8, n] are read coalesced (128 consecutive n per row).
 //
-// Warp roles (384 threads, persistent CTA, one per SM):
-//   warps 0-3   dequant: packed int4 (smem) -> fp16 -> TMEM A stage        [fused]
-//   warps 4-7   epilogue: TMEM D -> +bias -> GELU -> +residual -> fp16 -> global
-//   warp  8     TMA producer: x tiles (+ Wt tiles in dense mode)
-//   warp  9     MMA issuer (one thread): tcgen05.mma kind::f16, commit -> mbarriers
-//   warp 10     TMA producer: packed-weight tiles                           [fused]
-//   warp 11     TMEM allocator
+// Warp roles (448 threads, persistent CTA, one per SM):
+//   warps 0-3   dequant set 0 (even k-blocks): packed int4 (smem) -> fp16 -> TMEM A stage
+//   warps 4-7   epilogue: TMEM D -> +bias -> GELU -> fp16 -> smem transpose -> +residual -> global
+//   warps 8-11  dequant set 1 (odd k-blocks)                                   [fused mode]
+//   warp 12     TMA producer: packed-weight tiles + x tiles (+ Wt tiles in dense mode)
+//   warp 13     TMEM allocator; one thread issues tcgen05.mma kind::f16 and commits -> mbarriers
 //
 // Dequant arithmetic is bit-identical to dequant.cu / oracle "stepwise" form:
 //   p = fma(1024+q, s, -1024 s)  == fp16(q*s)  (single rounding of the exact product)
@@ -37,7 +36,8 @@ namespace {
 
 constexpr int kBN = 128;        // output features per tile (UMMA M)
 constexpr int kBK = 64;         // k per pipeline stage (one 128-byte swizzle row of fp16)
-constexpr int kThreads = 384;
+constexpr int kThreads = 448;   // 14 warps, see the role table above
+constexpr int kWarpTma = 12, kWarpMma = 13;
 constexpr int kWStageBytes = 8 * kBN * 4;   // packed int4 tile: 8 words x 128 n
 constexpr int kAStageBytes = kBN * kBK * 2; // dense fp16 Wt tile
 
@@ -127,8 +127,13 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int NT = N / kBN;
   const int MT = (M + BM - 1) / BM;
   const int num_tiles = NT * MT;
+  // k-blocks this CTA walks through, over all of its tiles (tile i of this CTA is
+  // blockIdx.x + i * gridDim.x)
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int total_kb = my_tiles * num_kb;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < C::kXStages; ++i) {
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], 1);
@@ -147,51 +152,45 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
   }
-  if (warp == 11) tmem_alloc(tmem_slot, 512);
+  if (warp == kWarpMma) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    // ===================== TMA producer: x (and dense Wt) =====================
+  if (warp == kWarpTma) {
+    // ===================== TMA producer: x tiles + weight tiles =====================
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+      int xs = 0, ws = 0;
+      uint32_t xph = 0, wph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n_tile = t % NT, m_tile = t / NT;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&x_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&x_full[s], C::kXStageBytes + (FUSED ? 0 : kAStageBytes));
-          tma_load_2d(sx + s * C::kXStageBytes, &map_x, &x_full[s], kb * kBK, m_tile * BM);
+          if (FUSED) {
+            // packed weights first: the dequant warps are the longer leg of the pipeline
+            mbar_wait(&w_empty[ws], wph ^ 1);
+            mbar_arrive_expect_tx(&w_full[ws], kWStageBytes);
+            tma_load_2d(sw + ws * kWStageBytes, &map_w, &w_full[ws], n_tile * kBN, kb * 8);
+            if (++ws == C::kWStages) { ws = 0; wph ^= 1; }
+          }
+          mbar_wait(&x_empty[xs], xph ^ 1);
+          mbar_arrive_expect_tx(&x_full[xs], C::kXStageBytes + (FUSED ? 0 : kAStageBytes));
+          tma_load_2d(sx + xs * C::kXStageBytes, &map_x, &x_full[xs], kb * kBK, m_tile * BM);
           if (!FUSED)
-            tma_load_2d(sw + s * kAStageBytes, &map_w, &x_full[s], kb * kBK, n_tile * kBN);
-          if (++s == C::kXStages) { s = 0; ph ^= 1; }
+            tma_load_2d(sw + xs * kAStageBytes, &map_w, &x_full[xs], kb * kBK, n_tile * kBN);
+          if (++xs == C::kXStages) { xs = 0; xph ^= 1; }
         }
       }
     }
-  } else if (warp == 10) {
-    // ===================== TMA producer: packed weights =====================
-    if (FUSED && lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_tile = t % NT;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&w_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&w_full[s], kWStageBytes);
-          tma_load_2d(sw + s * kWStageBytes, &map_w, &w_full[s], n_tile * kBN, kb * 8);
-          if (++s == C::kWStages) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 9) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop convergently (so stage indices, descriptors and TMEM
+    // addresses are warp-uniform and live in uniform registers); one elected lane issues.
+    {
       constexpr uint32_t idesc = make_idesc_f16(kBN, BM, 0);
       int xs = 0, as = 0;
       uint32_t xph = 0, aph = 0;
@@ -208,113 +207,124 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           tc_fence_after();
           const uint64_t b_desc =
               make_smem_desc(smem_u32(sx + xs * C::kXStageBytes), 0, 1024, kLayoutSw128);
-          if (FUSED) {
-            const uint32_t a_tmem = tmem_base + C::kTmemABase + as * 32;
+          const uint32_t a_tmem = tmem_base + C::kTmemABase + as * 32;
+          const uint64_t a_desc =
+              make_smem_desc(smem_u32(sw + xs * kAStageBytes), 0, 1024, kLayoutSw128);
+          if (elect_one()) {
+            if (FUSED) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              tc_mma_ts(d_tmem, a_tmem + k * 8, b_desc + (k * 32 >> 4), idesc, (kb | k) != 0);
-          } else {
-            const uint64_t a_desc =
-                make_smem_desc(smem_u32(sw + xs * kAStageBytes), 0, 1024, kLayoutSw128);
+              for (int k = 0; k < kBK / 16; ++k)
+                tc_mma_ts(d_tmem, a_tmem + k * 8, b_desc + (k * 32 >> 4), idesc, (kb | k) != 0);
+            } else {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              tc_mma_ss(d_tmem, a_desc + (k * 32 >> 4), b_desc + (k * 32 >> 4), idesc,
-                        (kb | k) != 0);
+              for (int k = 0; k < kBK / 16; ++k)
+                tc_mma_ss(d_tmem, a_desc + (k * 32 >> 4), b_desc + (k * 32 >> 4), idesc,
+                          (kb | k) != 0);
+            }
+            tc_commit(&x_empty[xs]);
+            if (FUSED) tc_commit(&a_empty[as]);
+            if (kb == num_kb - 1) tc_commit(&acc_full[ab]);
           }
-          tc_commit(&x_empty[xs]);
+          __syncwarp();
           if (FUSED) {
-            tc_commit(&a_empty[as]);
             if (++as == C::kAStages) { as = 0; aph ^= 1; }
           }
           if (++xs == C::kXStages) { xs = 0; xph ^= 1; }
         }
-        tc_commit(&acc_full[ab]);
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 || (warp >= 8 && warp < 12)) {
     // ===================== dequant warps (fused mode) =====================
+    // Two sets of four warps (set 0 = warps 0-3, set 1 = warps 8-11; warp % 4 = TMEM lane
+    // quadrant) take alternate k-blocks, so one set's unpack + tcgen05.st latency (~500 clk
+    // per k-block for a single warp) hides behind the other's and behind the 384-clk MMA.
     if (FUSED) {
-      const int tid = threadIdx.x;  // 0..127 == TMEM lane == n within tile
-      int ws = 0, as = 0;
-      uint32_t wph = 0, aph = 0;
-      const int kb_per_group = groupsize / kBK;
+      static_assert(C::kWStages == 8 && (C::kAStages & (C::kAStages - 1)) == 0, "ring sizes");
+      const int set = warp >> 3;
+      const int q4 = warp & 3;
+      const int tid = q4 * 32 + lane;  // 0..127 == TMEM lane == n within tile
       const int zwords = N / 8;
       const int zshift = (tid & 7) * 4;
-      // group constants are fetched one group ahead (across tile boundaries too) as raw
-      // loads: nothing may depend on them until the group starts, or the "prefetch" stalls
-      // the warp for a full L2 round trip every group
+      // (scale, zero word) of a k-block, addressed by the CTA-wide k-block counter
+      auto group_ptrs = [&](int kbc, const __half*& sp, const int32_t*& zp) {
+        const int tl = kbc / num_kb, kb = kbc - tl * num_kb;
+        const int t = blockIdx.x + tl * gridDim.x;
+        const int n = (t % NT) * kBN + tid;
+        const int g = (kb * kBK) / groupsize;
+        sp = scales + static_cast<int64_t>(g) * N + n;
+        zp = qzeros + static_cast<int64_t>(g) * zwords + (n >> 3);
+      };
+      // constants are fetched one own-k-block ahead as raw loads (nothing depends on them
+      // until that k-block starts, so the loads never stall the warp)
       __half s_next = __float2half(0.f);
       uint32_t zw_next = 0;
-      if (static_cast<int>(blockIdx.x) < num_tiles) {
-        const int n_first = (blockIdx.x % NT) * kBN + tid;
-        s_next = scales[n_first];
-        zw_next = static_cast<uint32_t>(qzeros[n_first >> 3]);
+      if (set < total_kb) {
+        const __half* sp;
+        const int32_t* zp;
+        group_ptrs(set, sp, zp);
+        s_next = *sp;
+        zw_next = static_cast<uint32_t>(*zp);
       }
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n = (t % NT) * kBN + tid;
-        const int t_next = t + gridDim.x;
-        const int n_next_tile = (t_next % NT) * kBN + tid;
-        uint32_t s2 = 0, c2 = 0, nzs2 = 0;
-        int kb_in_group = 0, g = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (kb_in_group == 0) {
-            const __half s = s_next;
-            const uint32_t z = (zw_next >> zshift) & 0xF;
-            const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
-            s2 = h2_dup(s);
-            c2 = h2_dup(__hneg(__hmul_rn(s, __float2half(1024.f))));
-            nzs2 = h2_dup(__hneg(zs));
-            ++g;
-            if (g * groupsize < K) {
-              s_next = scales[static_cast<int64_t>(g) * N + n];
-              zw_next = static_cast<uint32_t>(qzeros[static_cast<int64_t>(g) * zwords + (n >> 3)]);
-            } else if (t_next < num_tiles) {
-              s_next = scales[n_next_tile];
-              zw_next = static_cast<uint32_t>(qzeros[n_next_tile >> 3]);
-            }
-          }
-          if (++kb_in_group == kb_per_group) kb_in_group = 0;
-
-          mbar_wait(&w_full[ws], wph);
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(sw + ws * kWStageBytes) + tid;
-          uint32_t q[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) q[r] = wp[r * kBN];
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&w_empty[ws]);
-          if (++ws == C::kWStages) { ws = 0; wph ^= 1; }
-
-          uint32_t out[32];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const uint32_t w = q[r];
-            // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q
-            uint32_t a = nib_to_h2(w), b = nib_to_h2(w >> 4), c = nib_to_h2(w >> 8),
-                     d = nib_to_h2(w >> 12);
-            a = h2_add(h2_fma(a, s2, c2), nzs2);
-            b = h2_add(h2_fma(b, s2, c2), nzs2);
-            c = h2_add(h2_fma(c, s2, c2), nzs2);
-            d = h2_add(h2_fma(d, s2, c2), nzs2);
-            out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
-            out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
-            out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)
-            out[4 * r + 3] = prmt(c, d, 0x7632);  // (k6,k7)
-          }
-          mbar_wait(&a_empty[as], aph ^ 1);
-          tc_fence_after();
-          tmem_st_x32(tmem_base + C::kTmemABase + as * 32 + (static_cast<uint32_t>(warp * 32) << 16), out);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[as]);
-          if (++as == C::kAStages) { as = 0; aph ^= 1; }
+      for (int kbc = set; kbc < total_kb; kbc += 2) {
+        const __half s = s_next;
+        const uint32_t z = (zw_next >> zshift) & 0xF;
+        const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
+        const uint32_t s2 = h2_dup(s);
+        const uint32_t c2 = h2_dup(__hneg(__hmul_rn(s, __float2half(1024.f))));
+        const uint32_t nzs2 = h2_dup(__hneg(zs));
+        if (kbc + 2 < total_kb) {
+          const __half* sp;
+          const int32_t* zp;
+          group_ptrs(kbc + 2, sp, zp);
+          s_next = *sp;
+          zw_next = static_cast<uint32_t>(*zp);
         }
+        const int ws = kbc & (C::kWStages - 1);
+        const uint32_t wph = (kbc / C::kWStages) & 1;
+        const int as = kbc & (C::kAStages - 1);
+        const uint32_t aph = (kbc / C::kAStages) & 1;
+
+        mbar_wait(&w_full[ws], wph);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sw + ws * kWStageBytes) + tid;
+        uint32_t q[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) q[r] = wp[r * kBN];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_empty[ws]);
+
+        uint32_t out[32];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint32_t w = q[r];
+          // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q
+          uint32_t a = nib_to_h2(w), b = nib_to_h2(w >> 4), c = nib_to_h2(w >> 8),
+                   d = nib_to_h2(w >> 12);
+          a = h2_add(h2_fma(a, s2, c2), nzs2);
+          b = h2_add(h2_fma(b, s2, c2), nzs2);
+          c = h2_add(h2_fma(c, s2, c2), nzs2);
+          d = h2_add(h2_fma(d, s2, c2), nzs2);
+          out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
+          out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
+          out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)
+          out[4 * r + 3] = prmt(c, d, 0x7632);  // (k6,k7)
+        }
+        mbar_wait(&a_empty[as], aph ^ 1);
+        tc_fence_after();
+        tmem_st_x32(tmem_base + C::kTmemABase + as * 32 + (static_cast<uint32_t>(q4 * 32) << 16), out);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
       }
     }
   } else if (warp < 8) {
     // ===================== epilogue warps =====================
     const int e = warp - 4;
     int lt = 0;
+    // 32(m) x 32(n) staging block of this warp: lanes own n, so the block is transposed
+    // through shared memory and written as 16-byte row segments (2-byte scattered global
+    // stores ran at <2 B/clk/SM).
+    __half* stage = reinterpret_cast<__half*>(sepi + e * 2048);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int n_tile = t % NT, m_tile = t / NT;
       const int n = n_tile * kBN + e * 32 + lane;
@@ -324,10 +334,6 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       mbar_wait(&acc_full[ab], acc_ph);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * BM + (static_cast<uint32_t>(e * 32) << 16);
-      // 32(m) x 32(n) staging block of this warp: lanes own n, so the block is
-      // transposed through shared memory and written as 16-byte row segments
-      // (2-byte scattered global stores ran at <2 B/clk/SM).
-      __half* stage = reinterpret_cast<__half*>(sepi + e * 2048);
 #pragma unroll 1
       for (int c = 0; c < BM / 32; ++c) {
         uint32_t r[32];
@@ -372,7 +378,7 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
