@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -222,13 +223,20 @@ def main():
     _lib.device_check(dev)
     torch.backends.cudnn.benchmark = True
 
-    enc = random_quantized_encoder(args.model, 4, 128, seed=0, device=dev)
+    enc_eager = random_quantized_encoder(args.model, 4, 128, seed=0, device=dev)
     B = args.batch
     nbuf = 3
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     inputs = [torch.randn(B, 3, 1024, 1024, device=dev, generator=gen).half() for _ in range(nbuf)]
     host_in = [t.cpu().pin_memory() for t in inputs]
     host_out = torch.empty(B, 256, 64, 64, dtype=torch.float16).pin_memory()
+    if args.no_graph:
+        enc = enc_eager
+    else:
+        from sam_quantization_b200.launcher import GraphedEncoder
+
+        enc = GraphedEncoder(enc_eager, inputs[0])   # public API: captured forward, replayed per step
+    config["launch"] = "eager" if args.no_graph else "cuda-graph replay of the whole encoder forward"
 
     def barrier():
         if world > 1:
@@ -254,17 +262,22 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - launches0
+        if not args.no_graph:   # replays do not pass through the C ABI: count what the graph holds
+            launches = args.steps * enc.kernels_per_replay
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- end-to-end: host buffers, H2D + encoder + D2H per step ----------------------
         for i in range(2):
-            host_out.copy_(enc(host_in[i % nbuf].to(dev, non_blocking=True)), non_blocking=True)
+            host_out.copy_(enc(host_in[i % nbuf] if not args.no_graph else host_in[i % nbuf].to(dev)), non_blocking=True)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
         for i in range(args.steps):
-            x = host_in[i % nbuf].to(dev, non_blocking=True)
-            host_out.copy_(enc(x), non_blocking=True)
+            if args.no_graph:
+                y = enc(host_in[i % nbuf].to(dev, non_blocking=True))
+            else:
+                y = enc(host_in[i % nbuf])          # H2D straight into the graph's static input
+            host_out.copy_(y, non_blocking=True)
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
@@ -286,7 +299,7 @@ def main():
         import sam_quantization_b200.quant_linear as ql
         ql.ops.qlinear = timed_qlinear
         for i in range(2):
-            enc(inputs[i % nbuf])
+            enc_eager(inputs[i % nbuf])
         torch.cuda.synchronize()
         ops.qlinear = orig
         for s, t, fl in rec:
@@ -333,7 +346,7 @@ def main():
         if not args.no_cpu_baseline:
             try:
                 nb = 8
-                pcpu = cpu_reference_prepare(args.model, packed_state_cpu(enc), nb)
+                pcpu = cpu_reference_prepare(args.model, packed_state_cpu(enc_eager), nb)
                 ips, sec, cores = cpu_reference_images_per_s(args.model, pcpu, nb)
                 line["cpu_baseline"] = {
                     "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
