@@ -268,6 +268,74 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+
+// ---- thread-block clusters / CTA pairs (cta_group::2) ----------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS' ClusterBarrier does:
+// an explicit .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per arrive
+// (measured: halved the 2-CTA GEMM).  What is handed over here is tensor memory, ordered by
+// tcgen05.fence::before_thread_sync / ::after_thread_sync, not generic-proxy stores.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// In a CTA pair the two CTAs' shared::cluster windows differ in bit 24; clearing it
+// addresses the same offset in the even (leader) CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to the
+// LEADER CTA's mbarrier (both CTAs of the pair execute it for their half of the operand).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask),
+        "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of all prior cta_group::2 MMAs, arriving on the barrier at the same offset in
+// every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[tmem, 128 rows per CTA] . B[smem, N/2 rows per CTA]^T  (M = 256)
+__device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // named barrier among `nthreads` threads
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

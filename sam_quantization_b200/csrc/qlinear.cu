@@ -24,9 +24,17 @@
 // Dequant arithmetic is bit-identical to dequant.cu / oracle "stepwise" form:
 //   p = fma(1024+q, s, -1024 s)  == fp16(q*s)  (single rounding of the exact product)
 //   w = p - fp16((z+1)*s)                      (fp16 rounding)
-#include "common.cuh"
+#include "qlinear_common.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace samq {
+
+int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales,
+                        const int32_t* qzeros, const __half* bias, const __half* residual,
+                        __half* y, int64_t M, int K, int N, int groupsize, int epilogue,
+                        int num_sms, cudaStream_t st);
 
 int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* scales,
                    const int32_t* g_idx, void* w_out, int K, int N, int bits, int groupsize,
@@ -56,45 +64,6 @@ struct Cfg {
   static_assert(kAStages >= 2 || !FUSED, "need at least two TMEM A stages");
   static_assert(BM % 32 == 0 && BM <= 256, "BM");
 };
-
-// Exact-erf GELU, x * Phi(x), with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on
-// erf):  Phi(x) = 1 - g (x >= 0) | g (x < 0),  g = 0.5 erfc(|x|/sqrt2) = poly(t) exp(-x^2/2),
-// t = 1/(1 + p |x|/sqrt2).  gelu(x) = max(x, 0) - g |x|.  Max abs error 3.4e-7 over [-12, 12]
-// (checked in tests/test_gelu_approx.py): far below the fp16 output rounding.  14 instructions
-// (2 MUFU) instead of ~40 for erff, which made the lin1 epilogue issue-bound.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
-  float poly = 0.5f * 1.061405429f;
-  poly = fmaf(poly, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  poly *= t;
-  const float u = ax * 0.84932180028801904272f;   // |x| * sqrt(log2(e) / 2)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
-  return fmaf(-(poly * e), ax, fmaxf(x, 0.f));
-}
-
-// (a & 0x000f000f) | 0x64006400  ->  two fp16 values 1024 + nibble
-__device__ __forceinline__ uint32_t nib_to_h2(uint32_t w) {
-  return lop3_and_or(w, 0x000f000fu, 0x64006400u);
-}
-__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_dup(__half h) {
-  const uint32_t u = __half_as_ushort(h);
-  return u | (u << 16);
-}
 
 template <int BM, bool FUSED, bool GELU>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -472,6 +441,18 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
   const bool fused = bits == 4 && g_idx == nullptr && groupsize % kBK == 0 &&
                      reinterpret_cast<uintptr_t>(qweight) % 16 == 0;
   if (fused) {
+    // CTA-pair kernel (cta_group::2) whenever the feature count tiles by 256 (every SAM layer);
+    // SAMQ_GEMM=1cta forces the single-CTA kernel (ablation / fallback for odd N)
+    static const bool force_1cta = [] {
+      const char* v = getenv("SAMQ_GEMM");
+      return v && strcmp(v, "1cta") == 0;
+    }();
+    if (N % 256 == 0 && !force_1cta)
+      return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
+                                 reinterpret_cast<const __half*>(bias),
+                                 reinterpret_cast<const __half*>(residual),
+                                 reinterpret_cast<__half*>(y), M, K, N, groupsize, epilogue,
+                                 num_sms(), st);
     return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
                                      reinterpret_cast<const __half*>(bias),
                                      reinterpret_cast<const __half*>(residual),
