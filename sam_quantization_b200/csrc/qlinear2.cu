@@ -143,114 +143,57 @@ qlinear2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else if (warp == kWarpMma2) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // early non-blocking probes of the next k-block's barriers overlap the MMA issue
+    // (see the 1-CTA kernel for the measurement behind this)
     if (leader) {
       constexpr uint32_t idesc = make_idesc_f16(2 * kBN2, BM, 0);
-      int xs = 0, as = 0;
+      int xs = 0, as = 0, kb = 0, lt = 0;
       uint32_t xph = 0, aph = 0;
-      int lt = 0;
-      for (int t = pair; t < num_tiles; t += npairs, ++lt) {
+      bool a_rdy = total_kb > 0 && mbar_test(&a_full[0], 0);
+      bool x_rdy = total_kb > 0 && mbar_test(&x_full[0], 0);
+      for (int kbc = 0; kbc < total_kb; ++kbc) {
         const int ab = lt & 1;
-        const uint32_t acc_ph = (lt >> 1) & 1;
-        mbar_wait(&acc_empty[ab], acc_ph ^ 1);
+        if (kb == 0) mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);
+        if (!a_rdy) mbar_wait(&a_full[as], aph);
+        if (!x_rdy) mbar_wait(&x_full[xs], xph);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * BM;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&a_full[as], aph);
-          mbar_wait(&x_full[xs], xph);
-          tc_fence_after();
-          const uint64_t b_desc =
-              make_smem_desc(smem_u32(sx + xs * C::kXStageBytes), 0, 1024, kLayoutSw128);
-          const uint32_t a_tmem = tmem_base + C::kTmemABase + as * 32;
-          if (elect_one()) {
+        const uint64_t b_desc =
+            make_smem_desc(smem_u32(sx + xs * C::kXStageBytes), 0, 1024, kLayoutSw128);
+        const uint32_t a_tmem = tmem_base + C::kTmemABase + as * 32;
+        int xs_n = xs + 1, as_n = as + 1;
+        uint32_t xph_n = xph, aph_n = aph;
+        if (xs_n == C::kXStages) { xs_n = 0; xph_n ^= 1; }
+        if (as_n == C::kAStages) { as_n = 0; aph_n ^= 1; }
+        const bool more = kbc + 1 < total_kb;
+        const bool a_rdy_n = more && mbar_test(&a_full[as_n], aph_n);
+        const bool x_rdy_n = more && mbar_test(&x_full[xs_n], xph_n);
+        if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK2 / 16; ++k)
-              tc_mma_ts_pair(d_tmem, a_tmem + k * 8, b_desc + (k * 32 >> 4), idesc, (kb | k) != 0);
-            tc_commit_pair(&x_empty[xs], 3);
-            tc_commit_pair(&a_empty[as], 3);
-            if (kb == num_kb - 1) tc_commit_pair(&acc_full[ab], 3);
-          }
-          __syncwarp();
-          if (++as == C::kAStages) { as = 0; aph ^= 1; }
-          if (++xs == C::kXStages) { xs = 0; xph ^= 1; }
+          for (int k = 0; k < kBK2 / 16; ++k)
+            tc_mma_ts_pair(d_tmem, a_tmem + k * 8, b_desc + (k * 32 >> 4), idesc, (kb | k) != 0);
+          tc_commit_pair(&x_empty[xs], 3);
+          tc_commit_pair(&a_empty[as], 3);
+          if (kb == num_kb - 1) tc_commit_pair(&acc_full[ab], 3);
         }
+        __syncwarp();
+        xs = xs_n; xph = xph_n;
+        as = as_n; aph = aph_n;
+        a_rdy = a_rdy_n;
+        x_rdy = x_rdy_n;
+        if (++kb == num_kb) { kb = 0; ++lt; }
       }
     }
   } else if (warp < 4 || (warp >= 8 && warp < 12)) {
     // ===================== dequant warps (both CTAs, own 128 features) =====================
-    const int set = warp >> 3;
-    const int q4 = warp & 3;
-    const int tid = q4 * 32 + lane;
-    const int zwords = N / 8;
-    const int zshift = (tid & 7) * 4;
-    auto group_ptrs = [&](int kbc, const __half*& sp, const int32_t*& zp) {
-      const int tl = kbc / num_kb, kb = kbc - tl * num_kb;
-      const int t = pair + tl * npairs;
-      const int n = (t % NT) * 2 * kBN2 + static_cast<int>(rank) * kBN2 + tid;
-      const int g = (kb * kBK2) / groupsize;
-      sp = scales + static_cast<int64_t>(g) * N + n;
-      zp = qzeros + static_cast<int64_t>(g) * zwords + (n >> 3);
-    };
-    __half s_next = __float2half(0.f);
-    uint32_t zw_next = 0;
-    if (set < total_kb) {
-      const __half* sp;
-      const int32_t* zp;
-      group_ptrs(set, sp, zp);
-      s_next = *sp;
-      zw_next = static_cast<uint32_t>(*zp);
-    }
-    for (int kbc = set; kbc < total_kb; kbc += 2) {
-      const __half s = s_next;
-      const uint32_t z = (zw_next >> zshift) & 0xF;
-      const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
-      const uint32_t s2 = h2_dup(s);
-      const uint32_t c2 = h2_dup(__hneg(__hmul_rn(s, __float2half(1024.f))));
-      const uint32_t nzs2 = h2_dup(__hneg(zs));
-      if (kbc + 2 < total_kb) {
-        const __half* sp;
-        const int32_t* zp;
-        group_ptrs(kbc + 2, sp, zp);
-        s_next = *sp;
-        zw_next = static_cast<uint32_t>(*zp);
-      }
-      const int ws = kbc & (C::kWStages - 1);
-      const uint32_t wph = (kbc / C::kWStages) & 1;
-      const int as = kbc & (C::kAStages - 1);
-      const uint32_t aph = (kbc / C::kAStages) & 1;
-
-      mbar_wait(&w_full[ws], wph);
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(sw + ws * kWStageBytes2) + tid;
-      uint32_t q[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) q[r] = wp[r * kBN2];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&w_empty[ws]);
-
-      uint32_t out[32];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const uint32_t w = q[r];
-        uint32_t a = nib_to_h2(w), b = nib_to_h2(w >> 4), c = nib_to_h2(w >> 8), d = nib_to_h2(w >> 12);
-        a = h2_add(h2_fma(a, s2, c2), nzs2);
-        b = h2_add(h2_fma(b, s2, c2), nzs2);
-        c = h2_add(h2_fma(c, s2, c2), nzs2);
-        d = h2_add(h2_fma(d, s2, c2), nzs2);
-        out[4 * r + 0] = prmt(a, b, 0x5410);
-        out[4 * r + 1] = prmt(c, d, 0x5410);
-        out[4 * r + 2] = prmt(a, b, 0x7632);
-        out[4 * r + 3] = prmt(c, d, 0x7632);
-      }
-      mbar_wait(&a_empty[as], aph ^ 1);
-      tc_fence_after();
-      tmem_st_x32(tmem_base + C::kTmemABase + as * 32 + (static_cast<uint32_t>(q4 * 32) << 16), out);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(&a_full[as]);
-        else mbar_arrive_cluster(lead_a_full + as * 8);
-      }
-    }
+    dequant_warp_loop<C::kWStages, C::kAStages, kWStageBytes2>(
+        warp >> 3, warp & 3, lane, total_kb, num_kb, N, groupsize, scales, qzeros, sw, w_full, w_empty,
+        a_empty, tmem_base + C::kTmemABase,
+        [&](int tl) { return ((pair + tl * npairs) % NT) * 2 * kBN2 + static_cast<int>(rank) * kBN2; },
+        [&](int as) {
+          if (leader) mbar_arrive(&a_full[as]);
+          else mbar_arrive_cluster(lead_a_full + as * 8);
+        });
   } else if (warp < 8) {
     // ===================== epilogue warps (both CTAs, own accumulator) =====================
     const int e = warp - 4;

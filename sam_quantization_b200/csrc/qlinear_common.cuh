@@ -44,5 +44,113 @@ __device__ __forceinline__ uint32_t h2_dup(__half h) {
   return u | (u << 16);
 }
 
+// non-blocking probe of an mbarrier phase (the blocking try_wait costs ~90 clk even when the
+// phase is already complete; probing early lets that latency overlap useful work)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// One dequant warp's main loop (shared by the 1-CTA and 2-CTA kernels).
+//
+// `set` (0/1) takes the CTA-wide k-blocks kbc = set, set+2, ...  For each of them the warp
+// (TMEM lane quadrant q4) reads its 8 packed words per thread from the weight ring, unpacks
+// to fp16 (bit-identical to dequant.cu) and writes TMEM A stage kbc % kAStages.
+//   n_of_tile(tl)  -> first output feature of this CTA in its tl-th tile
+//   arrive_full(as) -> signal "A stage written" to the MMA issuer (local or remote barrier)
+// No integer division on the per-k-block path: (tile, kb, group) are tracked incrementally
+// (two dependent runtime divisions per k-block cost ~250 clk of latency in the first version).
+template <int kWStages, int kAStages, int kWStageBytes, class NOfTile, class ArriveFull>
+__device__ __forceinline__ void dequant_warp_loop(
+    int set, int q4, int lane, int total_kb, int num_kb, int N, int groupsize,
+    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros, const uint8_t* sw,
+    uint64_t* w_full, uint64_t* w_empty, uint64_t* a_empty, uint32_t tmem_a_base,
+    NOfTile n_of_tile, ArriveFull arrive_full) {
+  static_assert((kWStages & (kWStages - 1)) == 0 && (kAStages & (kAStages - 1)) == 0, "ring sizes");
+  const int tid = q4 * 32 + lane;  // 0..127 == TMEM lane == feature within the CTA's tile
+  const int zwords = N / 8;
+  const int zshift = (tid & 7) * 4;
+  const int kb_per_group = groupsize / 64;
+
+  // cursor of the k-block whose constants are being PREFETCHED (one own-k-block ahead)
+  int p_tl = 0, p_kb = set, p_g = 0, p_kig = set;   // tile, kb in tile, group, kb in group
+  auto normalise = [&]() {
+    while (p_kb >= num_kb) { p_kb -= num_kb; ++p_tl; p_g = 0; p_kig = p_kb; }
+    while (p_kig >= kb_per_group) { p_kig -= kb_per_group; ++p_g; }
+  };
+  normalise();
+  __half s_next = __float2half(0.f);
+  uint32_t zw_next = 0;
+  auto prefetch = [&]() {
+    const int n = n_of_tile(p_tl) + tid;
+    s_next = scales[static_cast<int64_t>(p_g) * N + n];
+    zw_next = static_cast<uint32_t>(qzeros[static_cast<int64_t>(p_g) * zwords + (n >> 3)]);
+  };
+  if (set < total_kb) prefetch();
+
+  for (int kbc = set; kbc < total_kb; kbc += 2) {
+    const int ws = kbc & (kWStages - 1);
+    const uint32_t wph = (kbc / kWStages) & 1;
+    const int as = kbc & (kAStages - 1);
+    const uint32_t aph = (kbc / kAStages) & 1;
+    // early, non-blocking probes; their latency hides behind the constant setup / unpack
+    const bool w_ready = mbar_test(&w_full[ws], wph);
+    const bool a_ready = mbar_test(&a_empty[as], aph ^ 1);
+
+    const __half s = s_next;
+    const uint32_t z = (zw_next >> zshift) & 0xF;
+    const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
+    const uint32_t s2 = h2_dup(s);
+    const uint32_t c2 = h2_dup(__hneg(__hmul_rn(s, __float2half(1024.f))));
+    const uint32_t nzs2 = h2_dup(__hneg(zs));
+    if (kbc + 2 < total_kb) {   // raw loads for the next own k-block: nothing depends on them yet
+      p_kb += 2;
+      p_kig += 2;
+      normalise();
+      prefetch();
+    }
+
+    if (!w_ready) mbar_wait(&w_full[ws], wph);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sw + ws * kWStageBytes) + tid;
+    uint32_t q[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) q[r] = wp[r * 128];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&w_empty[ws]);
+
+    uint32_t out[32];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t w = q[r];
+      // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q
+      uint32_t a = nib_to_h2(w), b = nib_to_h2(w >> 4), c = nib_to_h2(w >> 8), d = nib_to_h2(w >> 12);
+      a = h2_add(h2_fma(a, s2, c2), nzs2);
+      b = h2_add(h2_fma(b, s2, c2), nzs2);
+      c = h2_add(h2_fma(c, s2, c2), nzs2);
+      d = h2_add(h2_fma(d, s2, c2), nzs2);
+      out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
+      out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
+      out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)
+      out[4 * r + 3] = prmt(c, d, 0x7632);  // (k6,k7)
+    }
+    if (!a_ready) mbar_wait(&a_empty[as], aph ^ 1);   // MMAs that read this A stage are done
+    tc_fence_after();
+    tmem_st_x32(tmem_a_base + as * 32 + (static_cast<uint32_t>(q4 * 32) << 16), out);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) arrive_full(as);
+  }
+}
+
 }  // namespace
 }  // namespace samq

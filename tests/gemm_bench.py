@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sam_quantization_b200 import ops, _lib
-from tests.gpu_util import rand_packed, dev
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gpu_util import rand_packed, dev
 
 M, K, N = (int(v) for v in sys.argv[1:4])
 epi = _lib.EPI_GELU if len(sys.argv) > 4 and sys.argv[4] == "gelu" else _lib.EPI_NONE
