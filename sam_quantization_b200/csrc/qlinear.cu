@@ -381,13 +381,11 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
   const bool fused = bits == 4 && g_idx == nullptr && groupsize % kBK == 0 &&
                      reinterpret_cast<uintptr_t>(qweight) % 16 == 0;
   if (fused) {
-    // CTA-pair kernel (cta_group::2) whenever the feature count tiles by 256 (every SAM layer);
-    // SAMQ_GEMM=1cta forces the single-CTA kernel (ablation / fallback for odd N)
-    static const bool force_1cta = [] {
-      const char* v = getenv("SAMQ_GEMM");
-      return v && strcmp(v, "1cta") == 0;
-    }();
-    if (N % 256 == 0 && !force_1cta)
+    // Two fused kernels exist: the single-CTA one (default: fastest measured, burst and
+    // sustained) and the CTA-pair one (cta_group::2, qlinear2.cu; halves x traffic and the
+    // issue overhead per SM, needs N % 256 == 0).  SAMQ_GEMM=2cta selects the pair kernel.
+    const char* variant = getenv("SAMQ_GEMM");
+    if (variant && strcmp(variant, "2cta") == 0 && N % 256 == 0)
       return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
                                  reinterpret_cast<const __half*>(bias),
                                  reinterpret_cast<const __half*>(residual),

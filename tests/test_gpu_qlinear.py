@@ -125,6 +125,27 @@ def test_module_forward_and_reference_entry_point(cuda_device):
         m(x.transpose(1, 2))          # non-contiguous, quant_linear.py:381
 
 
+@pytest.mark.parametrize("K,N,M", [(1280, 3840, 4900), (5120, 1280, 4096), (1280, 5120, 777)])
+@pytest.mark.parametrize("epilogue", ["none", "gelu"])
+def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, monkeypatch, K, N, M, epilogue):
+    """The cta_group::2 kernel (SAMQ_GEMM=2cta) must give bit-identical results to the default
+    single-CTA kernel (same operands, same fp32 accumulation order per output)."""
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=12)
+    tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
+    x = torch.randn(M, K, device=cuda_device).half()
+    b = torch.randn(N, device=cuda_device).half()
+    r = torch.randn(M, N, device=cuda_device).half()
+    epi = _lib.EPI_GELU if epilogue == "gelu" else _lib.EPI_NONE
+    monkeypatch.delenv("SAMQ_GEMM", raising=False)
+    y1 = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=epi, residual=r)
+    monkeypatch.setenv("SAMQ_GEMM", "2cta")
+    y2 = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=epi, residual=r)
+    assert torch.equal(y1, y2)
+    ref = oq.qlinear(x.cpu().numpy(), qw, qz, sc, 4, 128, b.cpu().numpy(), None, epilogue, r.cpu().numpy())
+    err, mag, cos = report(y2, ref)
+    assert err <= ULP * mag + 1e-6 and cos >= 0.99999
+
+
 def test_dense_ablation_path_equals_fused(cuda_device):
     K, N = 1280, 3840
     qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=11)
