@@ -143,6 +143,12 @@ int samq_layernorm_partition_fwd(const void* x, const void* gamma, const void* b
 int samq_unpartition_residual(const void* windows, const void* shortcut, void* out,
                               int B, int H, int W, int C, int ws, void* stream);
 
+/* Patch extraction for PatchEmbed (image_encoder.py:411-442): the conv16x16/stride16 is the
+ * GEMM  rows[(b,ph,pw), (c,i,j)] . Wconv[D, (c,i,j)]^T, so the image is re-laid-out once
+ * (x fp16 [B,C,H,W] -> out fp16 [B*(H/P)*(W/P), C*P*P]) and fed to samq_dense_linear_fwd with
+ * bias and the positional embedding as the residual. */
+int samq_patchify_fwd(const void* x, void* out, int B, int C, int H, int W, int P, void* stream);
+
 /* out = a + b over n fp16 elements (image_encoder.py:204; global-attention blocks). */
 int samq_add(const void* a, const void* b, void* out, int64_t n, void* stream);
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "samq_unpartition_residual": (
         c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "samq_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "samq_patchify_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

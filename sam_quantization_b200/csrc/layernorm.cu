@@ -151,6 +151,136 @@ add_kernel(const __half* a, const __half* b, __half* out, int64_t nvec) {
   *reinterpret_cast<H8*>(out + i * 8) = r;
 }
 
+// ---- fast path: C == NVEC * 256 (768 / 1024 / 1280 ...), two tokens per warp ----------
+// Each lane keeps NVEC 16-byte vectors per token in registers; both tokens' loads are
+// issued before any arithmetic, so a warp has 2 * NVEC * 512 B in flight (the generic kernel
+// above had half of that and twice the registers, and reached only ~40 % of HBM bandwidth).
+template <int NVEC>
+__device__ __forceinline__ void ln_token_from_regs(const uint4 (&raw)[NVEC], const __half* __restrict__ gamma,
+                                                   const __half* __restrict__ beta, __half* __restrict__ dst,
+                                                   float inv_c, float eps, int lane) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      sum += f.x + f.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * inv_c;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      const float d0 = f.x - mean, d1 = f.y - mean;
+      var += d0 * d0 + d1 * d1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var * inv_c + eps);
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int v = lane + i * 32;
+    const uint4 g4 = *reinterpret_cast<const uint4*>(gamma + v * 8);
+    const uint4 b4 = *reinterpret_cast<const uint4*>(beta + v * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw[i]);
+    const __half2* g = reinterpret_cast<const __half2*>(&g4);
+    const __half2* b = reinterpret_cast<const __half2*>(&b4);
+    uint4 o4;
+    __half2* o = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      const float2 gf = __half22float2(g[j]);
+      const float2 bf = __half22float2(b[j]);
+      o[j] = __floats2half2_rn((f.x - mean) * rstd * gf.x + bf.x, (f.y - mean) * rstd * gf.y + bf.y);
+    }
+    *reinterpret_cast<uint4*>(dst + v * 8) = o4;
+  }
+}
+
+// PARTITION == false: rows are tokens of x;  true: rows are OUTPUT tokens of the windowed
+// layout [B*nH*nW, ws, ws, C] (source token looked up, padding written as zeros).
+template <int NVEC, bool PARTITION>
+__global__ void __launch_bounds__(256)
+layernorm_fast_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                      const __half* __restrict__ beta, __half* __restrict__ y, int64_t rows, int B,
+                      int H, int W, int ws, int nH, int nW, float eps) {
+  constexpr int C = NVEC * 256;
+  const int lane = threadIdx.x & 31;
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  const __half* src[2];
+  bool live[2], pad[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int64_t r = r0 + t;
+    live[t] = r < rows;
+    pad[t] = false;
+    src[t] = x;
+    if (live[t]) {
+      if (PARTITION) {
+        const int j = static_cast<int>(r % ws);
+        int64_t q = r / ws;
+        const int i = static_cast<int>(q % ws);
+        q /= ws;
+        const int ww = static_cast<int>(q % nW);
+        q /= nW;
+        const int wh = static_cast<int>(q % nH);
+        const int b = static_cast<int>(q / nH);
+        const int h = wh * ws + i, w = ww * ws + j;
+        pad[t] = !(h < H && w < W);
+        if (!pad[t]) src[t] = x + ((static_cast<int64_t>(b) * H + h) * W + w) * C;
+      } else {
+        src[t] = x + r * C;
+      }
+    }
+  }
+  uint4 raw[2][NVEC];
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i)
+      raw[t][i] = (live[t] && !pad[t]) ? *reinterpret_cast<const uint4*>(src[t] + (lane + i * 32) * 8)
+                                       : make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    if (!live[t]) continue;
+    __half* dst = y + (r0 + t) * C;
+    if (pad[t]) {
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) *reinterpret_cast<uint4*>(dst + (lane + i * 32) * 8) = make_uint4(0, 0, 0, 0);
+    } else {
+      ln_token_from_regs<NVEC>(raw[t], gamma, beta, dst, 1.0f / C, eps, lane);
+    }
+  }
+}
+
+template <bool PARTITION>
+bool launch_ln_fast(const __half* x, const __half* g, const __half* b, __half* y, int64_t rows, int C, int B,
+                    int H, int W, int ws, int nH, int nW, float eps, cudaStream_t st) {
+  if (C % 256 != 0 || C > 2048) return false;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + 2 * wpb - 1) / (2 * wpb));
+#define SAMQ_LN_CASE(NV)                                                                              \
+  case NV:                                                                                            \
+    layernorm_fast_kernel<NV, PARTITION><<<grid, wpb * 32, 0, st>>>(x, g, b, y, rows, B, H, W, ws, nH, nW, eps); \
+    return true;
+  switch (C / 256) {
+    SAMQ_LN_CASE(1) SAMQ_LN_CASE(2) SAMQ_LN_CASE(3) SAMQ_LN_CASE(4) SAMQ_LN_CASE(5) SAMQ_LN_CASE(6)
+    SAMQ_LN_CASE(7) SAMQ_LN_CASE(8)
+  }
+#undef SAMQ_LN_CASE
+  return false;
+}
+
 int check_ln(const void* x, const void* g, const void* b, const void* y, int C, const char* who) {
   SAMQ_REQUIRE(x && g && b && y, SAMQ_ERR_BAD_ARG, "%s: null pointer", who);
   SAMQ_REQUIRE(C > 0 && C % 8 == 0 && C <= kMaxVec * 256, SAMQ_ERR_BAD_SHAPE,
@@ -171,6 +301,12 @@ extern "C" int samq_layernorm_fwd(const void* x, const void* gamma, const void* 
   if (rc != SAMQ_OK) return rc;
   SAMQ_REQUIRE(rows >= 0, SAMQ_ERR_BAD_SHAPE, "samq_layernorm_fwd: rows=%lld", (long long)rows);
   if (rows == 0) return SAMQ_OK;
+  if (launch_ln_fast<false>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(gamma),
+                            reinterpret_cast<const __half*>(beta), reinterpret_cast<__half*>(y), rows, C, 0, 0,
+                            0, 1, 1, 1, eps, reinterpret_cast<cudaStream_t>(stream))) {
+    count_launch();
+    return check_launch("layernorm_fast_kernel");
+  }
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
   layernorm_kernel<<<grid, wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -190,6 +326,12 @@ extern "C" int samq_layernorm_partition_fwd(const void* x, const void* gamma, co
                "samq_layernorm_partition_fwd: B=%d H=%d W=%d ws=%d", B, H, W, ws);
   const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
   const int64_t total = static_cast<int64_t>(B) * nH * nW * ws * ws;
+  if (launch_ln_fast<true>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(gamma),
+                           reinterpret_cast<const __half*>(beta), reinterpret_cast<__half*>(y), total, C, B, H, W,
+                           ws, nH, nW, eps, reinterpret_cast<cudaStream_t>(stream))) {
+    count_launch();
+    return check_launch("layernorm_fast_kernel<partition>");
+  }
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((total + wpb - 1) / wpb);
   layernorm_partition_kernel<<<grid, wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -217,6 +359,48 @@ extern "C" int samq_unpartition_residual(const void* windows, const void* shortc
       reinterpret_cast<__half*>(out), B, H, W, C, ws, nH, nW);
   count_launch();
   return check_launch("unpartition_residual_kernel");
+}
+
+namespace samq {
+namespace {
+// Non-overlapping P x P patches of an NCHW image as GEMM rows (PatchEmbed's conv16x16/16,
+// image_encoder.py:434-442, is exactly  rows x [C*P*P] . W^T):  out[(b,ph,pw), (c,i,j)] =
+// x[b, c, ph*P+i, pw*P+j].  One thread per 16-byte chunk; consecutive threads walk an image
+// row, so reads are contiguous and writes are whole 32-byte sectors.
+__global__ void __launch_bounds__(256)
+patchify_kernel(const __half* __restrict__ x, __half* __restrict__ out, int B, int C, int H, int W, int P) {
+  const int cpr = W / 8;                       // 16-byte chunks per image row
+  const int64_t total = static_cast<int64_t>(B) * C * H * cpr;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % cpr);
+  int64_t t = idx / cpr;
+  const int row = static_cast<int>(t % H);
+  t /= H;
+  const int c = static_cast<int>(t % C);
+  const int b = static_cast<int>(t / C);
+  const int col = chunk * 8;
+  const int ph = row / P, i = row % P, pw = col / P, j = col % P;
+  const uint4 v = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(b) * C + c) * H + row) * W + col);
+  const int64_t orow = (static_cast<int64_t>(b) * (H / P) + ph) * (W / P) + pw;
+  *reinterpret_cast<uint4*>(out + orow * (static_cast<int64_t>(C) * P * P) + (c * P + i) * P + j) = v;
+}
+}  // namespace
+}  // namespace samq
+
+extern "C" int samq_patchify_fwd(const void* x, void* out, int B, int C, int H, int W, int P, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(x && out, SAMQ_ERR_BAD_ARG, "samq_patchify_fwd: null pointer");
+  SAMQ_REQUIRE(B > 0 && C > 0 && P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_patchify_fwd: B=%d C=%d H=%d W=%d P=%d (P %% 8 == 0, H,W multiples of P)", B, C, H, W, P);
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16 == 0, SAMQ_ERR_BAD_ARG,
+               "samq_patchify_fwd: pointers must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * C * H * (W / 8);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  patchify_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), B, C, H, W, P);
+  count_launch();
+  return check_launch("patchify_kernel");
 }
 
 extern "C" int samq_add(const void* a, const void* b, void* out, int64_t n, void* stream) {

@@ -245,6 +245,19 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const uint32_t d_tmem = tmem_base + ab * BM + (static_cast<uint32_t>(e * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BM / 32; ++c) {
+        const int m0 = m_tile * BM + c * 32;
+        const int q = lane & 3;
+        // residual rows of this 32x32 block are requested first: their DRAM/L2 latency
+        // overlaps the TMEM load, the epilogue math and the shared-memory transpose
+        uint4 rv[4];
+        if (residual) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int m = m0 + it * 8 + (lane >> 2);
+            rv[it] = (m < M) ? *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(m) * N + (n_tile * kBN + e * 32 + q * 8))
+                             : make_uint4(0, 0, 0, 0);
+          }
+        }
         uint32_t r[32];
         tmem_ld_x32(d_tmem + c * 32, r);
         tmem_ld_wait();
@@ -261,8 +274,6 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           stage[j * 32 + lane] = __float2half_rn(v);
         }
         __syncwarp();
-        const int m0 = m_tile * BM + c * 32;
-        const int q = lane & 3;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int row = it * 8 + (lane >> 2);
@@ -271,11 +282,10 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + q * 8);
             const size_t off = static_cast<size_t>(m) * N + (n_tile * kBN + e * 32 + q * 8);
             if (residual) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(residual + off);
-              val.x = h2_add(val.x, rv.x);
-              val.y = h2_add(val.y, rv.y);
-              val.z = h2_add(val.z, rv.z);
-              val.w = h2_add(val.w, rv.w);
+              val.x = h2_add(val.x, rv[it].x);
+              val.y = h2_add(val.y, rv[it].y);
+              val.z = h2_add(val.z, rv[it].z);
+              val.w = h2_add(val.w, rv[it].w);
             }
             *reinterpret_cast<uint4*>(y + off) = val;
           }

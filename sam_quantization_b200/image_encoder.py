@@ -270,6 +270,7 @@ class ImageEncoderViT(nn.Module):
                 rel_pos_zero_init=rel_pos_zero_init,
                 window_size=window_size if i not in global_attn_indexes else 0,
                 input_size=(img_size // patch_size, img_size // patch_size)))
+        self._pos_cache = {}
         self.neck = nn.Sequential(
             nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False),
             LayerNorm2d(out_chans),
@@ -283,7 +284,50 @@ class ImageEncoderViT(nn.Module):
             x = blk(x)
         return x
 
+    # -- fused stem / neck -------------------------------------------------
+    def _fused_stem_ready(self, x: torch.Tensor) -> bool:
+        conv = self.patch_embed.proj
+        return (x.is_cuda and x.dtype == torch.float16 and len(self.blocks) > 0
+                and all(b._fused_ready() for b in self.blocks) and self.pos_embed is not None
+                and conv.weight.dtype == torch.float16 and conv.kernel_size == conv.stride
+                and conv.padding == (0, 0) and conv.kernel_size[0] == conv.kernel_size[1]
+                and conv.kernel_size[0] % 8 == 0 and conv.out_channels % 128 == 0
+                and (conv.in_channels * conv.kernel_size[0] ** 2) % 64 == 0 and conv.bias is not None)
+
+    def _stem_fused(self, x: torch.Tensor) -> torch.Tensor:
+        """PatchEmbed + pos_embed as one patch re-layout + one tcgen05 GEMM (bias and the
+        positional embedding ride in the epilogue) instead of cuDNN conv + permute + add."""
+        conv = self.patch_embed.proj
+        B = x.shape[0]
+        P = conv.kernel_size[0]
+        Hp, Wp = x.shape[2] // P, x.shape[3] // P
+        rows = ops.patchify(x.contiguous(), P)
+        key = (B, self.pos_embed.data_ptr(), self.pos_embed._version, str(x.device))
+        pos = self._pos_cache.get(key)
+        if pos is None:     # batch-expanded positional embedding = the GEMM's residual operand
+            pos = self.pos_embed.detach().expand(B, -1, -1, -1).contiguous()
+            self._pos_cache = {key: pos}
+        tok = ops.dense_linear(rows, conv.weight.view(conv.out_channels, -1), conv.bias, residual=pos)
+        return tok.view(B, Hp, Wp, conv.out_channels)
+
+    def _neck_fused(self, x: torch.Tensor) -> torch.Tensor:
+        """conv1x1 as a tcgen05 GEMM, LayerNorm2d as the token LayerNorm kernel (channels are
+        the last dim in NHWC), conv3x3 on cuDNN in channels_last (no layout copies)."""
+        c1, n1, c3, n2 = self.neck[0], self.neck[1], self.neck[2], self.neck[3]
+        B, H, W, D = x.shape
+        y = ops.dense_linear(x.view(-1, D), c1.weight.view(c1.out_channels, D))
+        y = ops.layernorm(y, n1.weight, n1.bias, n1.eps)
+        y = y.view(B, H, W, -1).permute(0, 3, 1, 2)                     # NCHW view, channels_last memory
+        y = F.conv2d(y, c3.weight.contiguous(memory_format=torch.channels_last), None, padding=c3.padding)
+        y = y.permute(0, 2, 3, 1).contiguous()                          # NHWC
+        y = ops.layernorm(y, n2.weight, n2.bias, n2.eps)
+        return y.permute(0, 3, 1, 2).contiguous()                       # NCHW like the reference
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._fused_stem_ready(x):
+            x = self._stem_fused(x)
+            x = self.forward_tokens(x)
+            return self._neck_fused(x)
         x = self.patch_embed(x)
         if self.pos_embed is not None:
             x = x + self.pos_embed

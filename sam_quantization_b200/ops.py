@@ -149,6 +149,18 @@ def unpartition_residual(windows: torch.Tensor, shortcut: torch.Tensor, window_s
     return out
 
 
+def patchify(x: torch.Tensor, patch: int) -> torch.Tensor:
+    """``[B, C, H, W]`` fp16 -> ``[B*(H/P)*(W/P), C*P*P]`` rows of non-overlapping patches."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x")
+    B, C, H, W = x.shape
+    with _dev_ctx(x):
+        out = torch.empty((B * (H // patch) * (W // patch), C * patch * patch), dtype=torch.float16, device=x.device)
+        _lib.check(_lib.load().samq_patchify_fwd(_lib.ptr(x), _lib.ptr(out), B, C, H, W, patch,
+                                                 _lib.stream_ptr(x.device)))
+    return out
+
+
 def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _lib.require_cuda(a, "a")
     _check_half(a, "a"); _check_half(b, "b")

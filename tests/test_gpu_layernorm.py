@@ -59,3 +59,20 @@ def test_unpartition_residual(cuda_device, B, H, W, C):
     ref = (sc.float() + oe.window_unpartition(win, 14, pad_hw, (H, W))).half()
     assert torch.equal(out.cpu(), ref)
     assert torch.equal(ops.add(x.to(cuda_device), sc.to(cuda_device)).cpu(), (x.float() + sc.float()).half())
+
+
+def test_patchify_and_fused_patch_embed(cuda_device):
+    """samq_patchify_fwd + dense GEMM == conv16x16/stride16 + permute + pos_embed add
+    (image_encoder.py:107-109, 434-442); oracle = fp32 conv on the CPU."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 64, 96, generator=g).half()
+    rows = ops.patchify(x.to(cuda_device), 16)
+    ref = torch.nn.functional.unfold(x.float(), kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 3 * 256).half()
+    assert torch.equal(rows.cpu(), ref)
+    w = (torch.randn(128, 3, 16, 16, generator=g) * 0.05).half()
+    b = torch.randn(128, generator=g).half()
+    pos = torch.randn(2, 4, 6, 128, generator=g).half()
+    y = ops.dense_linear(rows, w.view(128, -1).to(cuda_device), b.to(cuda_device), residual=pos.to(cuda_device))
+    conv = torch.nn.functional.conv2d(x.float(), w.float(), b.float(), stride=16).permute(0, 2, 3, 1) + pos.float()
+    err, mag, cos = report(y.view(2, 4, 6, 128), conv)
+    assert err <= 2.0 ** -9 * mag and cos > 0.99999
