@@ -91,9 +91,11 @@ int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
  * x, y, residual fp16 row-major; bias fp16 [N] or NULL; residual NULL or [M,N]
  * (may alias y).  fp32 accumulation on tcgen05 tensor cores.
  * bits == 4 with g_idx == NULL and groupsize % 64 == 0 runs the fused
- * unpack->TMEM->tcgen05 kernel; every other supported format (bits 2/3/8,
- * g_idx) needs `workspace` = K*N fp16 (device scratch, may be reused between
- * calls on the same stream) and runs unpack_dequant + the dense tcgen05 kernel.
+ * unpack->TMEM->tcgen05 kernel when M < 12288 or workspace == NULL; for longer M
+ * (where re-dequantising the weight tile for every 192-token tile costs more than
+ * reading fp16 weights from L2) and for every other format (bits 2/3/8, g_idx) it
+ * runs unpack_dequant into `workspace` (K*N fp16 device scratch, may be reused
+ * between calls on the same stream) followed by the dense tcgen05 kernel.
  * Requires K % 64 == 0, N % 128 == 0 (the reference asserts K % 128 == 0 and
  * N % 256 == 0, quant_linear.py:389-395). */
 int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,

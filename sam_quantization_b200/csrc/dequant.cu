@@ -122,6 +122,53 @@ unpack_dequant_kernel(const int32_t* __restrict__ qweight, const int32_t* __rest
   }
 }
 
+// ---- int4 fast path, transposed output Wt[N, K] (feeds the dense tcgen05 GEMM) -------------
+// A warp covers 8 output features x 64 k: lane = (feature l & 7, 16-k chunk l >> 3).  Reads of
+// one packed row touch whole 32-byte sectors (8 consecutive n); the 4 lanes of a feature write
+// 128 contiguous bytes.  Same arithmetic as above, on fp16 pairs (lop3 / fma / add), so the
+// result is bit-identical to the generic kernel and to the fused GEMM's operand.
+__global__ void __launch_bounds__(256)
+dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                           const __half* __restrict__ scales, __half* __restrict__ wt, int K, int N,
+                           int groupsize) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int kblocks = K >> 6;                          // 64-k blocks
+  const int nb = warp_global / kblocks, kb = warp_global - nb * kblocks;
+  const int n = nb * 8 + (lane & 7);
+  const int k0 = kb * 64 + (lane >> 3) * 16;
+  if (n >= N) return;
+  const int g = k0 / groupsize;
+  const __half s = scales[static_cast<int64_t>(g) * N + n];
+  const uint32_t zw = static_cast<uint32_t>(qzeros[static_cast<int64_t>(g) * (N >> 3) + (n >> 3)]);
+  const uint32_t z = (zw >> ((n & 7) * 4)) & 0xF;
+  const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
+  const uint32_t su = __half_as_ushort(s), s2 = su | (su << 16);
+  const uint32_t cu = __half_as_ushort(__hneg(__hmul_rn(s, __float2half(1024.f)))), c2 = cu | (cu << 16);
+  const uint32_t zu = __half_as_ushort(__hneg(zs)), nzs2 = zu | (zu << 16);
+  uint32_t out[8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint32_t w = static_cast<uint32_t>(qweight[static_cast<int64_t>((k0 >> 3) + r) * N + n]);
+    uint32_t q4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v;
+      asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(v) : "r"(w >> (4 * j)));
+      asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(v) : "r"(v), "r"(s2), "r"(c2));     // fp16(q*s)
+      asm("add.rn.f16x2 %0, %1, %2;" : "=r"(q4[j]) : "r"(v), "r"(nzs2));            // - fp16((z+1)*s)
+    }
+    // q4[j] = (k_j, k_{j+4}); regroup to adjacent k pairs
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(out[4 * r + 0]) : "r"(q4[0]), "r"(q4[1]));
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(out[4 * r + 1]) : "r"(q4[2]), "r"(q4[3]));
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(out[4 * r + 2]) : "r"(q4[0]), "r"(q4[1]));
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(out[4 * r + 3]) : "r"(q4[2]), "r"(q4[3]));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(wt + static_cast<int64_t>(n) * K + k0);
+  dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
 template <int BITS>
 static int launch_unpack(const int32_t* qweight, const int32_t* qzeros, const __half* scales,
                          const int32_t* g_idx, __half* w_out, int K, int N, int groupsize,
@@ -152,6 +199,12 @@ int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* sc
                  "unpack_dequant: w_out must be 16-byte aligned");
   const __half* s = reinterpret_cast<const __half*>(scales);
   __half* w = reinterpret_cast<__half*>(w_out);
+  if (bits == 4 && transposed && g_idx == nullptr && K % 64 == 0 && N % 8 == 0 && groupsize % 16 == 0) {
+    const int warps = (N / 8) * (K / 64);
+    dequant4_transposed_kernel<<<(warps + 7) / 8, 256, 0, st>>>(qweight, qzeros, s, w, K, N, groupsize);
+    count_launch();
+    return check_launch("dequant4_transposed_kernel");
+  }
   switch (bits) {
     case 2: return launch_unpack<2>(qweight, qzeros, s, g_idx, w, K, N, groupsize, transposed, st);
     case 3: return launch_unpack<3>(qweight, qzeros, s, g_idx, w, K, N, groupsize, transposed, st);

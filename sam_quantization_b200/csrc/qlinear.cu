@@ -391,16 +391,35 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
   const bool fused = bits == 4 && g_idx == nullptr && groupsize % kBK == 0 &&
                      reinterpret_cast<uintptr_t>(qweight) % 16 == 0;
   if (fused) {
-    // Two fused kernels exist: the single-CTA one (default: fastest measured, burst and
-    // sustained) and the CTA-pair one (cta_group::2, qlinear2.cu; halves x traffic and the
-    // issue overhead per SM, needs N % 256 == 0).  SAMQ_GEMM=2cta selects the pair kernel.
+    // Kernel choice for int4 (all sm_100a, all tcgen05):
+    //   fused 1-CTA  (default for M < kTwoKernelMinM): unpack in registers -> TMEM -> MMA.  Weight
+    //                bytes stay int4 all the way, which is what matters while the GEMM is short.
+    //   unpack-once + dense GEMM (default for M >= kTwoKernelMinM when a workspace is given):
+    //                every 128x192 tile of the fused kernel re-dequantises its weight tile, i.e.
+    //                M/192 times per weight; for long M that redundant ALU work (and its power)
+    //                costs more than reading fp16 weights from L2.  Measured sustained, M ~ 32-39k:
+    //                972 / 893 / 890 / 1008 vs 850 / 803 / 797 / 870 TFLOP/s (tests/gemm_two_kernel.py).
+    //   fused 2-CTA  (SAMQ_GEMM=2cta): cta_group::2 pair kernel, qlinear2.cu.
+    // SAMQ_GEMM = fused | 2cta | dense forces one of them (ablations, tests).
+    constexpr int64_t kTwoKernelMinM = 12288;
     const char* variant = getenv("SAMQ_GEMM");
+    const bool force_fused = variant && strcmp(variant, "fused") == 0;
+    const bool force_dense = variant && strcmp(variant, "dense") == 0;
     if (variant && strcmp(variant, "2cta") == 0 && N % 256 == 0)
       return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
                                  reinterpret_cast<const __half*>(bias),
                                  reinterpret_cast<const __half*>(residual),
                                  reinterpret_cast<__half*>(y), M, K, N, groupsize, epilogue,
                                  num_sms(), st);
+    if (workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0 && !force_fused &&
+        (force_dense || M >= kTwoKernelMinM)) {
+      rc = unpack_dequant(qweight, qzeros, scales, nullptr, workspace, K, N, 4, groupsize, 1, st);
+      if (rc != SAMQ_OK) return rc;
+      return launch_qlinear<192, false>(x, workspace, nullptr, nullptr,
+                                        reinterpret_cast<const __half*>(bias),
+                                        reinterpret_cast<const __half*>(residual),
+                                        reinterpret_cast<__half*>(y), M, K, N, K, epilogue, st);
+    }
     return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
                                      reinterpret_cast<const __half*>(bias),
                                      reinterpret_cast<const __half*>(residual),

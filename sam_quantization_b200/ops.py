@@ -7,11 +7,16 @@ and launches the CUDA kernel on torch's current stream.  No eager fallback exist
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
+
+
+#: M from which samq_qlinear_fwd switches int4 from the fused kernel to unpack-once + dense GEMM
+TWO_KERNEL_MIN_M = 12288
 
 
 def _dev_ctx(t: torch.Tensor):
@@ -79,7 +84,10 @@ def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales
         if M == 0:
             return y
         fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
-        ws = None if fused else torch.empty(K * N, dtype=torch.float16, device=x.device)
+        # scratch for the dequantised weight: always for the non-int4 formats; for int4 only when
+        # M is long enough that the library prefers unpack-once + dense GEMM (see csrc/qlinear.cu)
+        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or os.environ.get("SAMQ_GEMM") == "dense"
+        ws = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
         _lib.check(_lib.load().samq_qlinear_fwd(
             _lib.ptr(x2), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx),
             _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), _lib.ptr(ws), M, K, N, bits, groupsize,

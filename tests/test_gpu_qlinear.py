@@ -79,11 +79,16 @@ def test_int4_act_order(cuda_device):
 
 
 @pytest.mark.parametrize("K,N", [(1280, 3840), (1280, 5120), (5120, 1280)])
-def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, K, N):
+@pytest.mark.parametrize("variant", ["auto", "fused"])
+def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, monkeypatch, K, N, variant):
     """At BASELINE's largest M the oracle is replaced by a size-independent identity:
     the fused kernel must equal an fp32 GEMM (torch, on the GPU) of the bit-exact dequantised
     weight (itself pinned to the oracle by test_gpu_dequant)."""
     M = 32768
+    if variant == "fused":
+        monkeypatch.setenv("SAMQ_GEMM", "fused")
+    else:
+        monkeypatch.delenv("SAMQ_GEMM", raising=False)
     qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=8)
     tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
     x = torch.randn(M, K, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(0)).half()
@@ -144,6 +149,24 @@ def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, monkeypatch, K, N
     ref = oq.qlinear(x.cpu().numpy(), qw, qz, sc, 4, 128, b.cpu().numpy(), None, epilogue, r.cpu().numpy())
     err, mag, cos = report(y2, ref)
     assert err <= ULP * mag + 1e-6 and cos >= 0.99999
+
+
+def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, monkeypatch):
+    """M >= 12288 takes unpack-once + dense GEMM; it must equal the fused kernel bit for bit."""
+    K, N, M = 1280, 1280, 12288 + 77
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=13)
+    tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
+    x = torch.randn(M, K, device=cuda_device).half()
+    b = torch.randn(N, device=cuda_device).half()
+    monkeypatch.delenv("SAMQ_GEMM", raising=False)
+    y_auto = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=_lib.EPI_GELU)
+    monkeypatch.setenv("SAMQ_GEMM", "fused")
+    y_fused = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=_lib.EPI_GELU)
+    assert torch.equal(y_auto, y_fused)
+    # and the fast transposed int4 dequant kernel is bit-exact against the oracle
+    wt = ops.unpack_dequant(tq, tz, ts, 4, 128, transposed=True)
+    ref = oq.dequant(qw, qz, sc, 4, 128)
+    assert np.array_equal(wt.t().contiguous().cpu().numpy().view(np.uint16), ref.view(np.uint16))
 
 
 def test_dense_ablation_path_equals_fused(cuda_device):
