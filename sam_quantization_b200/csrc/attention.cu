@@ -24,6 +24,9 @@
 // fused_attention.py:323): K = 64 (128B-swizzle tile) + 16 (32B-swizzle tile).
 #include "common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace samq {
 namespace {
 
@@ -428,6 +431,336 @@ attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
   }
 }
 
+// ===========================================================================================
+// Windowed attention, second design: the whole 14x14 window (196 keys, padded to 208) is ONE
+// key tile, so the softmax is exact single-pass (no online rescaling), and the CTA is small
+// enough -- 95 KB of shared memory, 256 TMEM columns, <= 128 registers -- that TWO CTAs share
+// an SM: one CTA's softmax overlaps the other's TMA / MMA / prologue.  (The first design ran
+// one 130 KB / 512-column CTA per SM and was prologue-bound: 151 TFLOP/s.)
+//   TMEM columns: S [0,208) fp32  ->  P [0,104) fp16 pairs (aliases S, written chunk by chunk
+//   behind the read pointer);  O [128, 128+hd) is written by the PV MMAs only after every S
+//   column has been consumed;  rel-pos tables T_h [0,32), T_w [32,64) live there before S.
+//   Shared memory: Q | rel_pos_h | rel_pos_w | K (208 rows) | V (208 rows); the fp16 bounce
+//   buffers of the rel-pos tables alias the V region (V's TMA is issued after they are read).
+// ===========================================================================================
+template <int HD>
+struct WCfg {
+  static constexpr int E = 14, S = 196, SP = 208;    // keys padded to a multiple of 16
+  static constexpr int kTail = HD - 64;
+  static constexpr int kQMain = 128 * 128, kQTail = kTail ? 128 * 32 : 0, kQBytes = kQMain + kQTail;
+  static constexpr int kKMain = SP * 128, kKTail = kTail ? SP * 32 : 0;
+  static constexpr int kKMainPad = ((kKMain + 1023) / 1024) * 1024;          // 26624 -> 26624
+  static constexpr int kKBytes = kKMainPad + ((kKTail + 1023) / 1024) * 1024;
+  static constexpr int kRpMain = 32 * 128, kRpTail = kTail ? 32 * 32 : 0;
+  static constexpr int kRpBytes = ((kRpMain + kRpTail + 1023) / 1024) * 1024;
+  static constexpr int oQ = 0;
+  static constexpr int oRph = oQ + ((kQBytes + 1023) / 1024) * 1024;
+  static constexpr int oRpw = oRph + kRpBytes;
+  static constexpr int oK = oRpw + kRpBytes;
+  static constexpr int oV = oK + kKBytes;
+  static constexpr int oBars = oV + kKBytes;
+  static constexpr int kBounceWords = 17;                                   // per row, odd stride
+  static constexpr int kSmemBytes = oBars + 16 * 8 + 16 + 1024;
+  static_assert(2 * 128 * kBounceWords * 4 <= kKBytes, "bounce buffers must fit in the V region");
+  static constexpr int cS = 0, cTh = 0, cTw = 32, cO = 128;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kAttThreads, 2)
+attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_constant__ CUtensorMap map_q_tail,
+                const __grid_constant__ CUtensorMap map_kv_main, const __grid_constant__ CUtensorMap map_kv_tail,
+                const __grid_constant__ CUtensorMap map_rph_main, const __grid_constant__ CUtensorMap map_rph_tail,
+                const __grid_constant__ CUtensorMap map_rpw_main, const __grid_constant__ CUtensorMap map_rpw_tail,
+                __half* __restrict__ out, int heads, float scale, int relw_mode) {
+  using C = WCfg<HD>;
+  constexpr int E = C::E, S = C::S, SP = C::SP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem + C::oQ;
+  uint8_t* sRph = smem + C::oRph;
+  uint8_t* sRpw = smem + C::oRpw;
+  uint8_t* sK = smem + C::oK;
+  uint8_t* sV = smem + C::oV;
+  uint32_t* sTh = reinterpret_cast<uint32_t*>(sV);                       // aliases V (see above)
+  uint32_t* sTw = sTh + 128 * C::kBounceWords;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBars);
+  uint64_t* q_full = bars + 0;      // Q + rel-pos tables landed
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* t_full = bars + 3;      // T_h / T_w MMAs done
+  uint64_t* t_done = bars + 4;      // softmax warps copied T out of TMEM (count 4)
+  uint64_t* b_done = bars + 5;      // softmax warps read their bias values from the bounce (count 4)
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;      // count 4
+  uint64_t* o_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int D = heads * HD;
+  const int m0 = q_tile * 128;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(t_full, 1);
+    mbar_init(t_done, 4); mbar_init(b_done, 4); mbar_init(s_full, 1); mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, C::kQBytes + 2 * (C::kRpMain + C::kRpTail));
+      tma_load_3d(sQ, &map_q_main, q_full, head * HD, m0, b);
+      tma_load_2d(sRph, &map_rph_main, q_full, 0, 0);
+      tma_load_2d(sRpw, &map_rpw_main, q_full, 0, 0);
+      if (C::kTail) {
+        tma_load_3d(sQ + C::kQMain, &map_q_tail, q_full, head * HD + 64, m0, b);
+        tma_load_2d(sRph + C::kRpMain, &map_rph_tail, q_full, 64, 0);
+        tma_load_2d(sRpw + C::kRpMain, &map_rpw_tail, q_full, 64, 0);
+      }
+      mbar_arrive_expect_tx(k_full, C::kKMain + C::kKTail);
+      tma_load_3d(sK, &map_kv_main, k_full, D + head * HD, 0, b);
+      if (C::kTail) tma_load_3d(sK + C::kKMainPad, &map_kv_tail, k_full, D + head * HD + 64, 0, b);
+      mbar_wait(b_done, 0);                      // bounce buffers (aliasing V) are no longer needed
+      mbar_arrive_expect_tx(v_full, C::kKMain + C::kKTail);
+      tma_load_3d(sV, &map_kv_main, v_full, 2 * D + head * HD, 0, b);
+      if (C::kTail) tma_load_3d(sV + C::kKMainPad, &map_kv_tail, v_full, 2 * D + head * HD + 64, 0, b);
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc_t = make_idesc_f16(128, 32, 0);
+    constexpr uint32_t idesc_qk = make_idesc_f16(128, SP, 0);
+    constexpr uint32_t idesc_pv_main = make_idesc_f16(128, 64, 1);
+    constexpr uint32_t idesc_pv_tail = make_idesc_f16(128, 16, 1);
+    const uint64_t q_main = make_smem_desc(smem_u32(sQ), 0, 1024, kLayoutSw128);
+    const uint64_t q_tail = make_smem_desc(smem_u32(sQ + C::kQMain), 0, 256, kLayoutSw32);
+    auto mma_q_times = [&](uint32_t d_tmem, const uint8_t* b_main_ptr, const uint8_t* b_tail_ptr, uint32_t idesc,
+                           uint64_t* done_bar) {
+      const uint64_t b_main = make_smem_desc(smem_u32(b_main_ptr), 0, 1024, kLayoutSw128);
+      const uint64_t b_tail = make_smem_desc(smem_u32(b_tail_ptr), 0, 256, kLayoutSw32);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc, k > 0);
+        if (C::kTail) tc_mma_ss(d_tmem, q_tail, b_tail, idesc, 1);
+        if (done_bar) tc_commit(done_bar);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    mma_q_times(tmem_base + C::cTh, sRph, sRph + C::kRpMain, idesc_t, nullptr);
+    mma_q_times(tmem_base + C::cTw, sRpw, sRpw + C::kRpMain, idesc_t, t_full);
+    mbar_wait(k_full, 0);
+    mbar_wait(t_done, 0);
+    tc_fence_after();
+    mma_q_times(tmem_base + C::cS, sK, sK + C::kKMainPad, idesc_qk, s_full);
+    mbar_wait(v_full, 0);
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+    const uint64_t v_main0 = make_smem_desc(smem_u32(sV), C::kKMainPad, 1024, kLayoutSw128);
+    const uint64_t v_tail0 = make_smem_desc(smem_u32(sV + C::kKMainPad), 4096, 256, kLayoutSw32);
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < SP / 16; ++ks) {
+        tc_mma_ts(tmem_base + C::cO, tmem_base + ks * 8, v_main0 + (ks * 2048 >> 4), idesc_pv_main, ks > 0);
+        if (C::kTail)
+          tc_mma_ts(tmem_base + C::cO + 64, tmem_base + ks * 8, v_tail0 + (ks * 512 >> 4), idesc_pv_tail, ks > 0);
+      }
+      tc_commit(o_full);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ============================ softmax / epilogue ============================
+    const int e = warp - 4;
+    const int row = e * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(e * 32) << 16;
+    const int m = m0 + row;
+    const bool valid = m < S;
+    const bool warp_valid = (m0 + e * 32) < S;        // warp-uniform: any valid row in this warp
+    const int mh = valid ? m / E : 0, mw = valid ? m % E : 0;
+    const float c_scale = scale * kLog2e;
+
+    mbar_wait(t_full, 0);
+    tc_fence_after();
+    uint32_t* my_th = sTh + row * C::kBounceWords;
+    uint32_t* my_tw = sTw + row * C::kBounceWords;
+    float bh[E], bw[E];
+    if (warp_valid) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_base + C::cTh + lane_off, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) my_th[i] = pack_h2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+      tmem_ld_x32(tmem_base + C::cTw + lane_off, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) my_tw[i] = pack_h2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t_done);
+    {
+      const __half* th_row = reinterpret_cast<const __half*>(my_th);
+      const __half* tw_row = reinterpret_cast<const __half*>(my_tw);
+      const int rw = (relw_mode == SAMQ_RELW_UPSTREAM) ? mw : mh;
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        bh[k] = warp_valid ? kLog2e * __half2float(th_row[mh - k + E - 1]) : 0.f;
+        bw[k] = warp_valid ? kLog2e * __half2float(tw_row[rw - k + E - 1]) : 0.f;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(b_done);
+
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    const uint32_t s_tmem = tmem_base + C::cS + lane_off;
+    float l = 0.f;
+    if (warp_valid) {
+      // 7 steps of 2 key rows (28 keys): S columns [28i, 28i+28), bias = bh[2i | 2i+1] + bw[kw]
+      // ---- pass 1: row maximum over the 196 real keys ----
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        uint32_t r[32];
+        tmem_ld_x32(s_tmem + 28 * i, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 28; ++j)
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), c_scale, bw[j % E]) + bh[2 * i + (j >= E ? 1 : 0)]);
+      }
+      // (the bias is added as fma(s, c, bw) + bh so that nothing but the 28 table values is
+      // loop-invariant: summing bh + bw first made the compiler keep 196 sums alive and spill)
+#pragma unroll
+      for (int k = 0; k < E; ++k) bh[k] -= mx;
+      // ---- pass 2: P = 2^(x - max) as fp16 pairs, written behind the read pointer ----
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        uint32_t r[32];
+        tmem_ld_x32(s_tmem + 28 * i, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 28; j += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[j]), c_scale, bw[j % E]) + bh[2 * i + (j >= E ? 1 : 0)]);
+          const float p1 = ex2(fmaf(__uint_as_float(r[j + 1]), c_scale, bw[(j + 1) % E]) + bh[2 * i + (j + 1 >= E ? 1 : 0)]);
+          l += p0 + p1;
+          pk[j >> 1] = pack_h2(p0, p1);
+        }
+        pk[14] = 0;   // the two extra columns belong to the next step (rewritten there) or are
+        pk[15] = 0;   // the zero padding after key 195
+        tmem_st_x16(s_tmem + 14 * i, pk);   // 14i+15 < 28(i+1): never ahead of the read pointer
+      }
+      {
+        // padded keys 200..207 (P columns 100..103) must be exact zeros for the K = 208 PV MMA
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(s_tmem + 100), "r"(0u)
+                     : "memory");
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_full);
+
+    // ---- epilogue: O / l ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    if (warp_valid) {
+      const float inv_l = 1.f / l;
+      const uint32_t o_tmem = tmem_base + C::cO + lane_off;
+      __half* dst = out + (static_cast<size_t>(b) * S + (valid ? m : 0)) * D + head * HD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(o_tmem + c * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 o;
+            o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+            o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+            o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+            o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c * 32 + v * 8) = o;
+          }
+        }
+      }
+      if (C::kTail) {
+        uint32_t r[16];
+        tmem_ld_x16(o_tmem + 64, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            uint4 o;
+            o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+            o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+            o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+            o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + 64 + v * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <int HD>
+int launch_attn_win(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads, float scale,
+                    int relw_mode, cudaStream_t st) {
+  using C = WCfg<HD>;
+  const int D = heads * HD;
+  const uint64_t row_bytes = static_cast<uint64_t>(3) * D * 2;
+  uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {row_bytes, row_bytes * C::S};
+  uint32_t q_main[3] = {64, 128, 1}, q_tail[3] = {16, 128, 1};
+  uint32_t kv_main[3] = {64, static_cast<uint32_t>(C::SP), 1}, kv_tail[3] = {16, static_cast<uint32_t>(C::SP), 1};
+  const CUtensorMap* mq = get_tensor_map_nd(qkv, 3, dims, strides, q_main, 2, 3);
+  const CUtensorMap* mkv = get_tensor_map_nd(qkv, 3, dims, strides, kv_main, 2, 3);
+  const CUtensorMap* mh = get_tensor_map_2d(rph, 27, HD, HD * 2, 32, 64, 2, 3);
+  const CUtensorMap* mw = get_tensor_map_2d(rpw, 27, HD, HD * 2, 32, 64, 2, 3);
+  if (!mq || !mkv || !mh || !mw) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap *mqt = mq, *mkvt = mkv, *mht = mh, *mwt = mw;
+  if (C::kTail) {
+    mqt = get_tensor_map_nd(qkv, 3, dims, strides, q_tail, 2, 1);
+    mkvt = get_tensor_map_nd(qkv, 3, dims, strides, kv_tail, 2, 1);
+    mht = get_tensor_map_2d(rph, 27, HD, HD * 2, 32, 16, 2, 1);
+    mwt = get_tensor_map_2d(rpw, 27, HD, HD * 2, 32, 16, 2, 1);
+    if (!mqt || !mkvt || !mht || !mwt) return SAMQ_ERR_LAUNCH;
+  }
+  auto kern = attn_win_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_win smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
+      return SAMQ_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  dim3 grid(2, heads, B);
+  kern<<<grid, kAttThreads, C::kSmemBytes, st>>>(*mq, *mqt, *mkv, *mkvt, *mh, *mht, *mw, *mwt,
+                                                reinterpret_cast<__half*>(out), heads, scale, relw_mode);
+  count_launch();
+  return check_launch("attn_win_kernel");
+}
+
 template <int HD, bool WIN>
 int launch_attn(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads,
                 float scale, int relw_mode, cudaStream_t st) {
@@ -491,10 +824,14 @@ extern "C" int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, cons
   const bool glob = (H == 64 && W == 64), win = (H == 14 && W == 14);
   SAMQ_REQUIRE(glob || win, SAMQ_ERR_BAD_SHAPE,
                "samq_attn_relpos_fwd: (H,W)=(%d,%d) not supported ((64,64) or (14,14))", H, W);
+  const char* wv = getenv("SAMQ_ATTN_WIN");   // "v1": first windowed design (two key tiles), ablation only
+  const bool win_v1 = wv && strcmp(wv, "v1") == 0;
   if (hd == 64) {
-    return glob ? launch_attn<64, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
-                : launch_attn<64, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+    if (glob) return launch_attn<64, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+    return win_v1 ? launch_attn<64, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
+                  : launch_attn_win<64>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
   }
-  return glob ? launch_attn<80, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
-              : launch_attn<80, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+  if (glob) return launch_attn<80, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+  return win_v1 ? launch_attn<80, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
+                : launch_attn_win<80>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
 }
