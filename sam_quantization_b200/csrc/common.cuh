@@ -323,6 +323,18 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask)
       ::"r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
 }
+// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] . B[smem, N/2 rows per CTA]^T  (M = 256)
+__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem, both CTAs] (+)= A[tmem, 128 rows per CTA] . B[smem, N/2 rows per CTA]^T  (M = 256)
 __device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
                                                uint32_t idesc, uint32_t accumulate) {

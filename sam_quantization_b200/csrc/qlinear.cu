@@ -36,6 +36,9 @@ int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales
                         __half* y, int64_t M, int K, int N, int groupsize, int epilogue,
                         int num_sms, cudaStream_t st);
 
+int launch_dense_pair(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
+                      int64_t M, int K, int N, int epilogue, int num_sms, cudaStream_t st);
+
 int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* scales,
                    const int32_t* g_idx, void* w_out, int K, int N, int bits, int groupsize,
                    int transposed, cudaStream_t st);
@@ -345,6 +348,17 @@ int launch_qlinear(const void* x, const void* w, const __half* scales, const int
   return check_launch("qlinear_kernel");
 }
 
+// dense fp16 GEMM: the CTA-pair 256x256 kernel when the feature count tiles by 256 and there is
+// enough work for it, else the single-CTA 128x192 kernel (SAMQ_DENSE=1cta forces the latter)
+int launch_dense(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
+                 int64_t M, int K, int N, int epilogue, cudaStream_t st) {
+  const char* v = getenv("SAMQ_DENSE");
+  const bool force_1cta = v && strcmp(v, "1cta") == 0;
+  if (N % 256 == 0 && M >= 2048 && !force_1cta)
+    return launch_dense_pair(x, wt, bias, residual, y, M, K, N, epilogue, num_sms(), st);
+  return launch_qlinear<192, false>(x, wt, nullptr, nullptr, bias, residual, y, M, K, N, K, epilogue, st);
+}
+
 int check_common(const void* x, const void* y, int64_t M, int K, int N, int epilogue,
                  const char* who) {
   SAMQ_REQUIRE(x && y, SAMQ_ERR_BAD_ARG, "%s: null pointer", who);
@@ -368,10 +382,8 @@ extern "C" int samq_dense_linear_fwd(const void* x, const void* wt, const void* 
   if (rc != SAMQ_OK) return rc;
   SAMQ_REQUIRE(wt && reinterpret_cast<uintptr_t>(wt) % 16 == 0, SAMQ_ERR_BAD_ARG,
                "samq_dense_linear_fwd: wt must be non-null and 16-byte aligned");
-  return launch_qlinear<192, false>(x, wt, nullptr, nullptr, reinterpret_cast<const __half*>(bias),
-                                    reinterpret_cast<const __half*>(residual),
-                                    reinterpret_cast<__half*>(y), M, K, N, K, epilogue,
-                                    reinterpret_cast<cudaStream_t>(stream));
+  return launch_dense(x, wt, reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(residual),
+                      reinterpret_cast<__half*>(y), M, K, N, epilogue, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
@@ -415,10 +427,9 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
         (force_dense || M >= kTwoKernelMinM)) {
       rc = unpack_dequant(qweight, qzeros, scales, nullptr, workspace, K, N, 4, groupsize, 1, st);
       if (rc != SAMQ_OK) return rc;
-      return launch_qlinear<192, false>(x, workspace, nullptr, nullptr,
-                                        reinterpret_cast<const __half*>(bias),
-                                        reinterpret_cast<const __half*>(residual),
-                                        reinterpret_cast<__half*>(y), M, K, N, K, epilogue, st);
+      return launch_dense(x, workspace, reinterpret_cast<const __half*>(bias),
+                          reinterpret_cast<const __half*>(residual), reinterpret_cast<__half*>(y), M, K, N,
+                          epilogue, st);
     }
     return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
                                      reinterpret_cast<const __half*>(bias),
@@ -430,8 +441,7 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
                g_idx ? " with g_idx" : "");
   rc = unpack_dequant(qweight, qzeros, scales, g_idx, workspace, K, N, bits, groupsize, 1, st);
   if (rc != SAMQ_OK) return rc;
-  return launch_qlinear<192, false>(x, workspace, nullptr, nullptr,
-                                    reinterpret_cast<const __half*>(bias),
-                                    reinterpret_cast<const __half*>(residual),
-                                    reinterpret_cast<__half*>(y), M, K, N, K, epilogue, st);
+  return launch_dense(x, workspace, reinterpret_cast<const __half*>(bias),
+                      reinterpret_cast<const __half*>(residual), reinterpret_cast<__half*>(y), M, K, N, epilogue,
+                      st);
 }
