@@ -104,6 +104,19 @@ int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzero
                      int64_t M, int K, int N, int bits, int groupsize,
                      int epilogue, void* stream);
 
+/* proj GEMM fused with window_unpartition + crop + residual add
+ * (QuantAttention.forward's o_proj, fused_attention.py:147, followed by
+ * image_encoder.py:201-204, 309-333):  x holds the attention output of the WINDOWED
+ * tokens, fp16 [B*nH*nW*ws*ws, K] (nH = ceil(H/ws)); the result row of window token
+ * (b, wh, ww, i, j) is written to image token (b, wh*ws+i, ww*ws+j) of y fp16 [B, H, W, N]
+ * as  shortcut[b,h,w,:] + (x.W + bias); padding tokens are dropped.  Other arguments as
+ * samq_qlinear_fwd.  y may alias shortcut. */
+int samq_qlinear_unpartition_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                                 const void* scales, const int32_t* g_idx, const void* bias,
+                                 const void* shortcut, void* y, void* workspace, int B, int H,
+                                 int W, int ws, int K, int N, int bits, int groupsize,
+                                 void* stream);
+
 /* Dense fp16 GEMM on the same tcgen05 kernel: y = epi(x . Wt^T + bias) + residual
  * with Wt fp16 [N, K] (already dequantised).  Used for the ablation "dequantise
  * once, then GEMM" and by samq_qlinear_fwd for the non-int4 formats. */

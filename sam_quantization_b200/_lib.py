@@ -44,6 +44,11 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p],
     ),
+    "samq_qlinear_unpartition_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    ),
     "samq_dense_linear_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],

@@ -34,10 +34,10 @@ namespace samq {
 int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales,
                         const int32_t* qzeros, const __half* bias, const __half* residual,
                         __half* y, int64_t M, int K, int N, int groupsize, int epilogue,
-                        int num_sms, cudaStream_t st);
+                        const RowMap& rowmap, int num_sms, cudaStream_t st);
 
 int launch_dense_pair(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
-                      int64_t M, int K, int N, int epilogue, int num_sms, cudaStream_t st);
+                      int64_t M, int K, int N, int epilogue, const RowMap& rowmap, int num_sms, cudaStream_t st);
 
 int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* scales,
                    const int32_t* g_idx, void* w_out, int K, int N, int bits, int groupsize,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N,
-               int K, int groupsize) {
+               int K, int groupsize, const RowMap rowmap) {
   using C = Cfg<BM, FUSED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -249,18 +249,8 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < BM / 32; ++c) {
         const int m0 = m_tile * BM + c * 32;
-        const int q = lane & 3;
-        // residual rows of this 32x32 block are requested first: their DRAM/L2 latency
-        // overlaps the TMEM load, the epilogue math and the shared-memory transpose
-        uint4 rv[4];
-        if (residual) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = m0 + it * 8 + (lane >> 2);
-            rv[it] = (m < M) ? *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(m) * N + (n_tile * kBN + e * 32 + q * 8))
-                             : make_uint4(0, 0, 0, 0);
-          }
-        }
+        EpiBlock<GELU> blk;
+        blk.prefetch(m0, M, N, n_tile * kBN + e * 32, lane, residual, rowmap);
         uint32_t r[32];
         tmem_ld_x32(d_tmem + c * 32, r);
         tmem_ld_wait();
@@ -270,30 +260,7 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]) + bv;
-          if (GELU) v = gelu_erf(v);
-          stage[j * 32 + lane] = __float2half_rn(v);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + (lane >> 2);
-          const int m = m0 + row;
-          if (m < M) {
-            uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + q * 8);
-            const size_t off = static_cast<size_t>(m) * N + (n_tile * kBN + e * 32 + q * 8);
-            if (residual) {
-              val.x = h2_add(val.x, rv[it].x);
-              val.y = h2_add(val.y, rv[it].y);
-              val.z = h2_add(val.z, rv[it].z);
-              val.w = h2_add(val.w, rv[it].w);
-            }
-            *reinterpret_cast<uint4*>(y + off) = val;
-          }
-        }
-        __syncwarp();
+        blk.finish(r, bv, stage, N, n_tile * kBN + e * 32, lane, residual != nullptr, y);
       }
     }
   }
@@ -320,7 +287,7 @@ int num_sms() {
 template <int BM, bool FUSED>
 int launch_qlinear(const void* x, const void* w, const __half* scales, const int32_t* qzeros,
                    const __half* bias, const __half* residual, __half* y, int64_t M, int K, int N,
-                   int groupsize, int epilogue, cudaStream_t st) {
+                   int groupsize, int epilogue, const RowMap& rowmap, cudaStream_t st) {
   using C = Cfg<BM, FUSED>;
   const CUtensorMap* mx = get_tensor_map_2d(x, static_cast<uint64_t>(M), K, static_cast<uint64_t>(K) * 2, BM, kBK, 2, 3);
   if (!mx) return SAMQ_ERR_LAUNCH;
@@ -343,7 +310,7 @@ int launch_qlinear(const void* x, const void* w, const __half* scales, const int
   const int64_t tiles = NT * MT;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(*mx, *mw, scales, qzeros, bias, residual, y,
-                                              static_cast<int>(M), N, K, groupsize);
+                                              static_cast<int>(M), N, K, groupsize, rowmap);
   count_launch();
   return check_launch("qlinear_kernel");
 }
@@ -351,12 +318,12 @@ int launch_qlinear(const void* x, const void* w, const __half* scales, const int
 // dense fp16 GEMM: the CTA-pair 256x256 kernel when the feature count tiles by 256 and there is
 // enough work for it, else the single-CTA 128x192 kernel (SAMQ_DENSE=1cta forces the latter)
 int launch_dense(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
-                 int64_t M, int K, int N, int epilogue, cudaStream_t st) {
+                 int64_t M, int K, int N, int epilogue, const RowMap& rowmap, cudaStream_t st) {
   const char* v = getenv("SAMQ_DENSE");
   const bool force_1cta = v && strcmp(v, "1cta") == 0;
   if (N % 256 == 0 && M >= 2048 && !force_1cta)
-    return launch_dense_pair(x, wt, bias, residual, y, M, K, N, epilogue, num_sms(), st);
-  return launch_qlinear<192, false>(x, wt, nullptr, nullptr, bias, residual, y, M, K, N, K, epilogue, st);
+    return launch_dense_pair(x, wt, bias, residual, y, M, K, N, epilogue, rowmap, num_sms(), st);
+  return launch_qlinear<192, false>(x, wt, nullptr, nullptr, bias, residual, y, M, K, N, K, epilogue, rowmap, st);
 }
 
 int check_common(const void* x, const void* y, int64_t M, int K, int N, int epilogue,
@@ -374,32 +341,25 @@ int check_common(const void* x, const void* y, int64_t M, int K, int N, int epil
 
 }  // namespace samq
 
-extern "C" int samq_dense_linear_fwd(const void* x, const void* wt, const void* bias,
-                                     const void* residual, void* y, int64_t M, int K, int N,
-                                     int epilogue, void* stream) {
-  using namespace samq;
-  int rc = check_common(x, y, M, K, N, epilogue, "samq_dense_linear_fwd");
-  if (rc != SAMQ_OK) return rc;
-  SAMQ_REQUIRE(wt && reinterpret_cast<uintptr_t>(wt) % 16 == 0, SAMQ_ERR_BAD_ARG,
-               "samq_dense_linear_fwd: wt must be non-null and 16-byte aligned");
-  return launch_dense(x, wt, reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(residual),
-                      reinterpret_cast<__half*>(y), M, K, N, epilogue, reinterpret_cast<cudaStream_t>(stream));
-}
+namespace samq {
+namespace {
 
-extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
-                                const void* scales, const int32_t* g_idx, const void* bias,
-                                const void* residual, void* y, void* workspace, int64_t M, int K,
-                                int N, int bits, int groupsize, int epilogue, void* stream) {
-  using namespace samq;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// common implementation of samq_qlinear_fwd / samq_qlinear_unpartition_fwd
+int qlinear_impl(const char* who, const void* x, const int32_t* qweight, const int32_t* qzeros,
+                 const void* scales, const int32_t* g_idx, const void* bias, const void* residual, void* y,
+                 void* workspace, int64_t M, int K, int N, int bits, int groupsize, int epilogue,
+                 const RowMap& rowmap, cudaStream_t st) {
   SAMQ_REQUIRE(bits == 2 || bits == 3 || bits == 4 || bits == 8, SAMQ_ERR_UNSUPPORTED_BITS,
-               "samq_qlinear_fwd: bits must be 2, 3, 4 or 8 (got %d)", bits);
-  int rc = check_common(x, y, M, K, N, epilogue, "samq_qlinear_fwd");
+               "%s: bits must be 2, 3, 4 or 8 (got %d)", who, bits);
+  int rc = check_common(x, y, M, K, N, epilogue, who);
   if (rc != SAMQ_OK) return rc;
-  SAMQ_REQUIRE(qweight && qzeros && scales, SAMQ_ERR_BAD_ARG, "samq_qlinear_fwd: null weight pointer");
+  SAMQ_REQUIRE(qweight && qzeros && scales, SAMQ_ERR_BAD_ARG, "%s: null weight pointer", who);
   if (groupsize == -1) groupsize = K;
   SAMQ_REQUIRE(groupsize > 0 && K % groupsize == 0, SAMQ_ERR_BAD_SHAPE,
-               "samq_qlinear_fwd: groupsize=%d must divide K=%d", groupsize, K);
+               "%s: groupsize=%d must divide K=%d", who, groupsize, K);
+  const __half* b = reinterpret_cast<const __half*>(bias);
+  const __half* r = reinterpret_cast<const __half*>(residual);
+  __half* out = reinterpret_cast<__half*>(y);
   const bool fused = bits == 4 && g_idx == nullptr && groupsize % kBK == 0 &&
                      reinterpret_cast<uintptr_t>(qweight) % 16 == 0;
   if (fused) {
@@ -409,8 +369,9 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
     //   unpack-once + dense GEMM (default for M >= kTwoKernelMinM when a workspace is given):
     //                every 128x192 tile of the fused kernel re-dequantises its weight tile, i.e.
     //                M/192 times per weight; for long M that redundant ALU work (and its power)
-    //                costs more than reading fp16 weights from L2.  Measured sustained, M ~ 32-39k:
-    //                972 / 893 / 890 / 1008 vs 850 / 803 / 797 / 870 TFLOP/s (tests/gemm_two_kernel.py).
+    //                costs more than reading fp16 weights from L2, and the dense GEMM can use the
+    //                256x256 CTA-pair tile.  Measured sustained at M = 32768 (tests/gemm_power.py):
+    //                fused 870, unpack + pair-dense 1199 TFLOP/s (cuBLAS fp16: 1193).
     //   fused 2-CTA  (SAMQ_GEMM=2cta): cta_group::2 pair kernel, qlinear2.cu.
     // SAMQ_GEMM = fused | 2cta | dense forces one of them (ablations, tests).
     constexpr int64_t kTwoKernelMinM = 12288;
@@ -418,30 +379,62 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
     const bool force_fused = variant && strcmp(variant, "fused") == 0;
     const bool force_dense = variant && strcmp(variant, "dense") == 0;
     if (variant && strcmp(variant, "2cta") == 0 && N % 256 == 0)
-      return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
-                                 reinterpret_cast<const __half*>(bias),
-                                 reinterpret_cast<const __half*>(residual),
-                                 reinterpret_cast<__half*>(y), M, K, N, groupsize, epilogue,
-                                 num_sms(), st);
+      return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros, b, r, out, M, K, N,
+                                 groupsize, epilogue, rowmap, num_sms(), st);
     if (workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0 && !force_fused &&
         (force_dense || M >= kTwoKernelMinM)) {
       rc = unpack_dequant(qweight, qzeros, scales, nullptr, workspace, K, N, 4, groupsize, 1, st);
       if (rc != SAMQ_OK) return rc;
-      return launch_dense(x, workspace, reinterpret_cast<const __half*>(bias),
-                          reinterpret_cast<const __half*>(residual), reinterpret_cast<__half*>(y), M, K, N,
-                          epilogue, st);
+      return launch_dense(x, workspace, b, r, out, M, K, N, epilogue, rowmap, st);
     }
-    return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros,
-                                     reinterpret_cast<const __half*>(bias),
-                                     reinterpret_cast<const __half*>(residual),
-                                     reinterpret_cast<__half*>(y), M, K, N, groupsize, epilogue, st);
+    return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros, b, r, out, M,
+                                     K, N, groupsize, epilogue, rowmap, st);
   }
   SAMQ_REQUIRE(workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, SAMQ_ERR_BAD_ARG,
-               "samq_qlinear_fwd: bits=%d%s needs a 16-byte aligned K*N fp16 workspace", bits,
-               g_idx ? " with g_idx" : "");
+               "%s: bits=%d%s needs a 16-byte aligned K*N fp16 workspace", who, bits, g_idx ? " with g_idx" : "");
   rc = unpack_dequant(qweight, qzeros, scales, g_idx, workspace, K, N, bits, groupsize, 1, st);
   if (rc != SAMQ_OK) return rc;
-  return launch_dense(x, workspace, reinterpret_cast<const __half*>(bias),
-                      reinterpret_cast<const __half*>(residual), reinterpret_cast<__half*>(y), M, K, N, epilogue,
-                      st);
+  return launch_dense(x, workspace, b, r, out, M, K, N, epilogue, rowmap, st);
+}
+
+}  // namespace
+}  // namespace samq
+
+extern "C" int samq_dense_linear_fwd(const void* x, const void* wt, const void* bias,
+                                     const void* residual, void* y, int64_t M, int K, int N,
+                                     int epilogue, void* stream) {
+  using namespace samq;
+  int rc = check_common(x, y, M, K, N, epilogue, "samq_dense_linear_fwd");
+  if (rc != SAMQ_OK) return rc;
+  SAMQ_REQUIRE(wt && reinterpret_cast<uintptr_t>(wt) % 16 == 0, SAMQ_ERR_BAD_ARG,
+               "samq_dense_linear_fwd: wt must be non-null and 16-byte aligned");
+  const RowMap identity = {0, 0, 0, 0, 0};
+  return launch_dense(x, wt, reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(residual),
+                      reinterpret_cast<__half*>(y), M, K, N, epilogue, identity,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                                const void* scales, const int32_t* g_idx, const void* bias,
+                                const void* residual, void* y, void* workspace, int64_t M, int K,
+                                int N, int bits, int groupsize, int epilogue, void* stream) {
+  const samq::RowMap identity = {0, 0, 0, 0, 0};
+  return samq::qlinear_impl("samq_qlinear_fwd", x, qweight, qzeros, scales, g_idx, bias, residual, y, workspace,
+                            M, K, N, bits, groupsize, epilogue, identity, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int samq_qlinear_unpartition_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                                            const void* scales, const int32_t* g_idx, const void* bias,
+                                            const void* shortcut, void* y, void* workspace, int B, int H,
+                                            int W, int ws, int K, int N, int bits, int groupsize,
+                                            void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(B > 0 && H > 0 && W > 0 && ws > 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_qlinear_unpartition_fwd: B=%d H=%d W=%d ws=%d", B, H, W, ws);
+  SAMQ_REQUIRE(shortcut != nullptr, SAMQ_ERR_BAD_ARG, "samq_qlinear_unpartition_fwd: shortcut is required");
+  const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
+  const int64_t M = static_cast<int64_t>(B) * nH * nW * ws * ws;
+  const RowMap rm = {ws, H, W, nH, nW};
+  return qlinear_impl("samq_qlinear_unpartition_fwd", x, qweight, qzeros, scales, g_idx, bias, shortcut, y,
+                      workspace, M, K, N, bits, groupsize, SAMQ_EPI_NONE, rm, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kThreads2, 1)
 qlinear2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                 const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                 const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N,
-                int K, int groupsize) {
+                int K, int groupsize, const RowMap rowmap) {
   using C = Cfg2<BM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -211,18 +211,8 @@ qlinear2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < BM / 32; ++c) {
         const int m0 = m_tile * BM + c * 32;
-        const int q = lane & 3;
-        // residual rows of this 32x32 block are requested first: their DRAM/L2 latency
-        // overlaps the TMEM load, the epilogue math and the shared-memory transpose
-        uint4 rv[4];
-        if (residual) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = m0 + it * 8 + (lane >> 2);
-            rv[it] = (m < M) ? *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(m) * N + (nb + q * 8))
-                             : make_uint4(0, 0, 0, 0);
-          }
-        }
+        EpiBlock<GELU> blk;
+        blk.prefetch(m0, M, N, nb, lane, residual, rowmap);
         uint32_t r[32];
         tmem_ld_x32(d_tmem + c * 32, r);
         tmem_ld_wait();
@@ -235,30 +225,7 @@ qlinear2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             else mbar_arrive_cluster(lead_acc_empty + ab * 8);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]) + bv;
-          if (GELU) v = gelu_erf(v);
-          stage[j * 32 + lane] = __float2half_rn(v);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + (lane >> 2);
-          const int m = m0 + row;
-          if (m < M) {
-            uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + q * 8);
-            const size_t off = static_cast<size_t>(m) * N + (nb + q * 8);
-            if (residual) {
-              val.x = h2_add(val.x, rv[it].x);
-              val.y = h2_add(val.y, rv[it].y);
-              val.z = h2_add(val.z, rv[it].z);
-              val.w = h2_add(val.w, rv[it].w);
-            }
-            *reinterpret_cast<uint4*>(y + off) = val;
-          }
-        }
-        __syncwarp();
+        blk.finish(r, bv, stage, N, nb, lane, residual != nullptr, y);
       }
     }
   }
@@ -279,7 +246,7 @@ qlinear2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales,
                         const int32_t* qzeros, const __half* bias, const __half* residual,
                         __half* y, int64_t M, int K, int N, int groupsize, int epilogue,
-                        int num_sms, cudaStream_t st) {
+                        const RowMap& rowmap, int num_sms, cudaStream_t st) {
   constexpr int BM = 192;
   using C = Cfg2<BM>;
   const CUtensorMap* mx = get_tensor_map_2d(x, static_cast<uint64_t>(M), K, static_cast<uint64_t>(K) * 2,
@@ -315,7 +282,7 @@ int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *mx, *mw, scales, qzeros, bias, residual, y,
-                                     static_cast<int>(M), N, K, groupsize);
+                                     static_cast<int>(M), N, K, groupsize, rowmap);
   count_launch();
   if (e != cudaSuccess) {
     set_error("qlinear2_kernel launch: %s", cudaGetErrorString(e));

@@ -3,6 +3,13 @@
 #include "common.cuh"
 
 namespace samq {
+
+// window-order GEMM row -> image-order row (see EpiBlock below); ws == 0 means identity.
+// Defined outside the anonymous namespace: it appears in cross-file launcher signatures.
+struct RowMap {
+  int ws, H, W, nH, nW;
+};
+
 namespace {
 
 // Exact-erf GELU, x * Phi(x), with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on
@@ -43,6 +50,72 @@ __device__ __forceinline__ uint32_t h2_dup(__half h) {
   const uint32_t u = __half_as_ushort(h);
   return u | (u << 16);
 }
+
+// ---- epilogue: one 32(token) x 32(feature) block per warp ------------------------------------
+// Optional row remap = window_unpartition + crop fused into the store
+// (image_encoder.py:201-204, 309-333): GEMM rows are tokens in window order
+// [B*nH*nW, ws, ws]; the destination row is the token's place in [B, H, W] and padding tokens
+// are dropped.  ws == 0 means identity.
+__device__ __forceinline__ int map_row(int m, int M, const RowMap& rm) {
+  if (m >= M) return -1;
+  if (rm.ws == 0) return m;
+  const int per_win = rm.ws * rm.ws;
+  const int win = m / per_win, within = m - win * per_win;
+  const int i = within / rm.ws, j = within - i * rm.ws;
+  const int ww = win % rm.nW, t = win / rm.nW;
+  const int wh = t % rm.nH, b = t / rm.nH;
+  const int h = wh * rm.ws + i, w = ww * rm.ws + j;
+  return (h < rm.H && w < rm.W) ? (b * rm.H + h) * rm.W + w : -1;
+}
+
+// Lanes own features (TMEM lanes), registers own tokens; the block is transposed through a
+// 2 KB shared-memory tile so that global accesses are 16-byte row segments.
+template <bool GELU>
+struct EpiBlock {
+  int dest[4];     // destination rows of the 4 row segments this lane stores (-1: skip)
+  uint4 rv[4];     // residual values for them
+
+  // before the TMEM load: destination rows (one map_row per lane, shuffled to where it is
+  // needed) and the residual loads, whose latency then overlaps the load + math + transpose
+  __device__ __forceinline__ void prefetch(int m0, int M, int N, int col0, int lane,
+                                           const __half* residual, const RowMap& rm) {
+    const int d = map_row(m0 + lane, M, rm);
+    const int q = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      dest[it] = __shfl_sync(0xffffffffu, d, it * 8 + (lane >> 2));
+      rv[it] = (residual && dest[it] >= 0)
+                   ? *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(dest[it]) * N + (col0 + q * 8))
+                   : make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  __device__ __forceinline__ void finish(const uint32_t (&r)[32], float bv, __half* stage, int N,
+                                         int col0, int lane, bool has_residual, __half* y) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = __uint_as_float(r[j]) + bv;
+      if (GELU) v = gelu_erf(v);
+      stage[j * 32 + lane] = __float2half_rn(v);
+    }
+    __syncwarp();
+    const int q = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (dest[it] >= 0) {
+        uint4 val = *reinterpret_cast<const uint4*>(stage + (it * 8 + (lane >> 2)) * 32 + q * 8);
+        if (has_residual) {   // fp16 add of two fp16 values, as the reference's `shortcut + x`
+          val.x = h2_add(val.x, rv[it].x);
+          val.y = h2_add(val.y, rv[it].y);
+          val.z = h2_add(val.z, rv[it].z);
+          val.w = h2_add(val.w, rv[it].w);
+        }
+        *reinterpret_cast<uint4*>(y + static_cast<size_t>(dest[it]) * N + (col0 + q * 8)) = val;
+      }
+    }
+    __syncwarp();
+  }
+};
 
 // non-blocking probe of an mbarrier phase (the blocking try_wait costs ~90 clk even when the
 // phase is already complete; probing early lets that latency overlap useful work)

@@ -15,7 +15,7 @@
 namespace samq {
 namespace {
 
-constexpr int kDThreads = 192;            // warps 0-3 epilogue, warp 4 TMA, warp 5 MMA + TMEM alloc
+constexpr int kDThreads = 320;            // warps 0-3 + 6-9 epilogue (two groups), warp 4 TMA, warp 5 MMA + TMEM alloc
 constexpr int kDWarpTma = 4, kDWarpMma = 5;
 constexpr int kDBM = 256;                 // tokens per pair tile (UMMA N)
 constexpr int kDBN = 128;                 // features per CTA   (UMMA M = 256 over the pair)
@@ -24,14 +24,15 @@ constexpr int kDStages = 6;
 constexpr int kDABytes = kDBN * kDBK * 2;          // 16 KB
 constexpr int kDXBytes = (kDBM / 2) * kDBK * 2;    // 16 KB (this CTA's half of the x tile)
 constexpr int kDStageBytes = kDABytes + kDXBytes;
-constexpr int kDEpiBytes = 4 * 2048;
+constexpr int kDEpiBytes = 8 * 2048;
 constexpr int kDSmemData = kDStages * kDStageBytes;
 constexpr int kDSmemBytes = kDSmemData + kDEpiBytes + (2 * kDStages + 4) * 8 + 16 + 1024;
 
 template <bool GELU>
 __global__ void __launch_bounds__(kDThreads, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-              const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N, int K) {
+              const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N, int K,
+              const RowMap rowmap) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -61,7 +62,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 8);
+      mbar_init(&acc_empty[i], 16);   // 8 epilogue warps of each CTA
     }
     fence_barrier_init();
   }
@@ -129,11 +130,14 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         if (++kb == num_kb) { kb = 0; ++lt; }
       }
     }
-  } else if (warp < 4) {
+  } else {
     // ===================== epilogue warps (both CTAs, own 128 features) =====================
-    const int e = warp;
+    // two groups of four warps (TMEM lane quadrant = warp % 4); group 0 drains token columns
+    // [0, 128), group 1 drains [128, 256) of the accumulator
+    const int e = warp & 3;
+    const int grp = warp < 4 ? 0 : 1;
     int lt = 0;
-    __half* stage = reinterpret_cast<__half*>(sepi + e * 2048);
+    __half* stage = reinterpret_cast<__half*>(sepi + (grp * 4 + e) * 2048);
     for (int t = pair; t < num_tiles; t += npairs, ++lt) {
       const int n_tile = t % NT, m_tile = t / NT;
       const int nb = n_tile * 2 * kDBN + static_cast<int>(rank) * kDBN + e * 32;
@@ -143,22 +147,15 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * kDBM + (static_cast<uint32_t>(e * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < kDBM / 32; ++c) {
+      for (int c = grp * (kDBM / 64); c < (grp + 1) * (kDBM / 64); ++c) {
         const int m0 = m_tile * kDBM + c * 32;
-        const int q = lane & 3;
-        uint4 rv[4];
-        if (residual) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = m0 + it * 8 + (lane >> 2);
-            rv[it] = (m < M) ? *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(m) * N + (nb + q * 8))
-                             : make_uint4(0, 0, 0, 0);
-          }
-        }
+        EpiBlock<GELU> blk;
+        blk.prefetch(m0, M, N, nb, lane, residual, rowmap);
         uint32_t r[32];
         tmem_ld_x32(d_tmem + c * 32, r);
         tmem_ld_wait();
-        if (c == kDBM / 32 - 1) {
+        if (c == (grp + 1) * (kDBM / 64) - 1) {
+          // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -166,30 +163,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             else mbar_arrive_cluster(lead_acc_empty + ab * 8);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(r[j]) + bv;
-          if (GELU) v = gelu_erf(v);
-          stage[j * 32 + lane] = __float2half_rn(v);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + (lane >> 2);
-          const int m = m0 + row;
-          if (m < M) {
-            uint4 val = *reinterpret_cast<const uint4*>(stage + row * 32 + q * 8);
-            const size_t off = static_cast<size_t>(m) * N + (nb + q * 8);
-            if (residual) {
-              val.x = h2_add(val.x, rv[it].x);
-              val.y = h2_add(val.y, rv[it].y);
-              val.z = h2_add(val.z, rv[it].z);
-              val.w = h2_add(val.w, rv[it].w);
-            }
-            *reinterpret_cast<uint4*>(y + off) = val;
-          }
-        }
-        __syncwarp();
+        blk.finish(r, bv, stage, N, nb, lane, residual != nullptr, y);
       }
     }
   }
@@ -205,7 +179,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 }  // namespace
 
 int launch_dense_pair(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
-                      int64_t M, int K, int N, int epilogue, int num_sms, cudaStream_t st) {
+                      int64_t M, int K, int N, int epilogue, const RowMap& rowmap, int num_sms, cudaStream_t st) {
   const CUtensorMap* mx = get_tensor_map_2d(x, static_cast<uint64_t>(M), K, static_cast<uint64_t>(K) * 2,
                                             kDBM / 2, kDBK, 2, 3);
   const CUtensorMap* mw = get_tensor_map_2d(wt, N, K, static_cast<uint64_t>(K) * 2, kDBN, kDBK, 2, 3);
@@ -238,7 +212,7 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *mx, *mw, bias, residual, y, static_cast<int>(M), N, K);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *mx, *mw, bias, residual, y, static_cast<int>(M), N, K, rowmap);
   count_launch();
   if (e != cudaSuccess) {
     set_error("dense2_kernel launch: %s", cudaGetErrorString(e));

@@ -55,12 +55,18 @@ class QuantAttention(nn.Module):
         return ops.attn_relpos(qkv, rph.contiguous(), rpw.contiguous(), B, H, W, self.num_heads,
                                self.scale, _RELW[self.relw_mode])
 
-    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                unpartition_window: int = 0) -> torch.Tensor:
         """Input ``[B, H, W, C]`` -> ``[B, H, W, C]`` (fused_attention.py:107-149).
-        ``residual`` (additive) is fused into the proj GEMM epilogue."""
+        Additive: ``residual`` is fused into the proj GEMM epilogue; with
+        ``unpartition_window = ws`` the input is windowed tokens ``[B*nWin, ws, ws, C]``, and the
+        proj epilogue also performs window_unpartition + crop, returning
+        ``residual + unpartition(attn)`` in the residual's ``[B, H, W, C]`` image order."""
         B, H, W, _ = x.shape
         qkv = self.qkv_proj(x)
         o = self.attention(qkv, B, H, W)
+        if unpartition_window:
+            return self.o_proj.forward_unpartition(o, residual, unpartition_window)
         if residual is not None:
             return self.o_proj(o, residual=residual)
         return self.o_proj(o)

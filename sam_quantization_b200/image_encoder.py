@@ -15,7 +15,7 @@ fused B200 path:
         LN1(+partition) -> qkv dequant-GEMM -> attention(+rel-pos) -> proj dequant-GEMM
         (+residual | unpartition+residual) -> LN2 -> lin1 dequant-GEMM(+bias+GELU)
         -> lin2 dequant-GEMM(+bias+residual)
-    i.e. 7 kernels per block, no eager elementwise op.
+    i.e. 6 kernels per block (+ the unpack of each weight at long M), no eager elementwise op.
   * Before quantization (fp32/fp16 nn.Linear) the module runs plain PyTorch, which is
     how weights are calibrated / packed and how the CPU tests drive the host logic.
     That eager path is NOT a fallback of the quantized path: a quantized block on a
@@ -214,8 +214,8 @@ class Block(nn.Module):
         if self.window_size > 0:
             ws = self.window_size
             xw, _ = ops.layernorm_partition(x, n1.weight, n1.bias, n1.eps, ws)
-            a = self.attn(xw)                                   # [B*nWin, ws, ws, C]
-            x = ops.unpartition_residual(a, x, ws)              # shortcut + unpartition(a)
+            # proj epilogue does window_unpartition + crop + residual: shortcut + unpartition(attn)
+            x = self.attn(xw, residual=x, unpartition_window=ws)
         else:
             xn = ops.layernorm(x, n1.weight, n1.bias, n1.eps)
             x = self.attn(xn, residual=x)                       # residual fused into proj

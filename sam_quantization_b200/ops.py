@@ -95,6 +95,34 @@ def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales
     return y
 
 
+def qlinear_unpartition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
+                        bits: int, groupsize: int, bias: Optional[torch.Tensor], shortcut: torch.Tensor,
+                        window_size: int, g_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``shortcut + window_unpartition(x @ W + bias)``: ``x`` is ``[B*nWin, ws, ws, K]`` (windowed
+    tokens), ``shortcut`` ``[B, H, W, N]``; returns ``[B, H, W, N]`` in image order."""
+    if bits not in (2, 3, 4, 8):
+        raise NotImplementedError("Only 2, 3, 4 and 8 bits are supported.")
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x"); _check_half(shortcut, "shortcut")
+    B, H, W, N = shortcut.shape
+    K = x.shape[-1]
+    ws = window_size
+    nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
+    M = B * nH * nW * ws * ws
+    assert x.numel() == M * K, "x must hold every windowed token of the batch"
+    assert qweight.shape[1] == N and qweight.shape[0] * 32 // bits == K
+    with _dev_ctx(x):
+        y = torch.empty_like(shortcut)
+        fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
+        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or os.environ.get("SAMQ_GEMM") == "dense"
+        wsp = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
+        _lib.check(_lib.load().samq_qlinear_unpartition_fwd(
+            _lib.ptr(x), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx), _lib.ptr(bias),
+            _lib.ptr(shortcut), _lib.ptr(y), _lib.ptr(wsp), B, H, W, ws, K, N, bits, groupsize,
+            _lib.stream_ptr(x.device)))
+    return y
+
+
 def dense_linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
                  epilogue: int = _lib.EPI_NONE, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``epi(x @ wt.T + bias) + residual`` with ``wt[N, K]`` fp16 (already dequantised)."""

@@ -107,6 +107,11 @@ class QuantLinear(nn.Module):
         return ops.qlinear(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
                            self.bias, self.g_idx, epilogue, residual)
 
+    def forward_unpartition(self, x: torch.Tensor, shortcut: torch.Tensor, window_size: int) -> torch.Tensor:
+        """``shortcut + window_unpartition(self(x))`` in one kernel (x: windowed tokens)."""
+        return ops.qlinear_unpartition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
+                                       self.bias, shortcut, window_size, self.g_idx)
+
     def dequantize(self, transposed: bool = False) -> torch.Tensor:
         """fp16 ``W[K, N]`` (``[N, K]`` if transposed) via ``samq_unpack_dequant``."""
         return ops.unpack_dequant(self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,

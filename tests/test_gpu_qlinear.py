@@ -178,3 +178,30 @@ def test_dense_ablation_path_equals_fused(cuda_device):
     wt = ops.unpack_dequant(tq, tz, ts, 4, 128, transposed=True)
     yd = ops.dense_linear(x, wt)
     assert torch.equal(y, yd)      # same fp16 operands, same fp32 accumulation order per tile
+
+
+@pytest.mark.parametrize("B,H,W,K,N,variant", [(1, 64, 64, 1280, 1280, "auto"), (3, 64, 64, 256, 256, "auto"),
+                                               (2, 20, 30, 128, 128, "auto"), (3, 64, 64, 1280, 1280, "dense"),
+                                               (2, 64, 64, 768, 768, "2cta")])
+def test_proj_with_fused_unpartition_and_residual(cuda_device, monkeypatch, B, H, W, K, N, variant):
+    """samq_qlinear_unpartition_fwd == shortcut + window_unpartition(x @ W + bias)
+    (image_encoder.py:201-204, 309-333), on every GEMM kernel variant."""
+    from oracle import encoder as oe
+    if variant == "auto":
+        monkeypatch.delenv("SAMQ_GEMM", raising=False)
+    else:
+        monkeypatch.setenv("SAMQ_GEMM", variant)
+    ws = 14
+    nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=21)
+    g = torch.Generator().manual_seed(5)
+    xw = torch.randn(B * nH * nW, ws, ws, K, generator=g).half()
+    sc_t = torch.randn(B, H, W, N, generator=g).half()
+    b = torch.randn(N, generator=g).half()
+    y = ops.qlinear_unpartition(xw.to(cuda_device), dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device),
+                                4, 128, b.to(cuda_device), sc_t.to(cuda_device), ws)
+    lin = torch.from_numpy(oq.qlinear(xw.numpy().reshape(-1, K), qw, qz, sc, 4, 128, b.numpy())).view(-1, ws, ws, N)
+    ref = sc_t.float() + oe.window_unpartition(lin.half().float(), ws, (nH * ws, nW * ws), (H, W))
+    err, mag, cos = report(y, ref)
+    assert y.shape == (B, H, W, N)
+    assert err <= 2 * ULP * mag and cos >= 0.99999
