@@ -26,6 +26,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace samq {
 namespace {
@@ -761,6 +762,545 @@ int launch_attn_win(const void* qkv, const void* rph, const void* rpw, void* out
   return check_launch("attn_win_kernel");
 }
 
+// ===========================================================================================
+// Global (64x64) attention, second design: two softmax warpgroups, software-pipelined.
+//
+// What the first design (attn_relpos_kernel<HD, false>) lost, measured with the clock64()
+// breakdown in tests/micro/attn_prof.cu: per 128-key tile the softmax warps spent ~900 clk in
+// "TMEM load -> scale + bias -> max" and ~1300 clk in "ex2 -> pack -> TMEM store", strictly one
+// after the other (every warp is in the same phase at the same time), against a MUFU floor of
+// 1024 clk and 640 clk of MMA; with head_dim 80 only two K/V stages fitted and the MMA warp
+// additionally waited ~1600 clk per tile for K.  This design:
+//   * a 128-key tile is two key rows kh = 2j, 2j+1 of the image; warpgroup g (warps 0-3 / 4-7)
+//     owns key row 2j+g, i.e. S columns [64g, 64g+64), for all 128 query rows, so a thread's
+//     whole share of a tile (64 scores) lives in registers: S is read from TMEM ONCE;
+//   * the scores of tile j+1 are fetched from TMEM before the ex2 phase of tile j and their
+//     scale / bias / max arithmetic is interleaved with that phase's MUFU stream;
+//   * S is triple-buffered in TMEM, so QK^T runs two tiles ahead of the softmax;
+//   * K and V have separate 3-slot rings (a K slot is released as soon as its QK^T retires);
+//     slot 2 of both aliases the rel-pos tables, which are dead after the prologue MMAs;
+//   * the bias tables go TMEM -> shared exactly once: bh as fp32 [key row][query] and bw as fp32
+//     [query][key col] in XOR-swizzled 16-byte chunks (conflict-free LDS.128).
+// The two threads of a query row exchange partial maxima through shared memory once per tile
+// (one 256-thread named barrier); partial row sums are combined at the end.
+// ===========================================================================================
+#ifdef SAMQ_ATTN_PROFILE
+// developer-only wait-time breakdown (tests/micro/attn_prof.cu); never compiled into libsamq.so
+__device__ long long g_attn_prof[12][8];
+#define PROF_DECL long long pt0 = 0, pstart = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_BEGIN pt0 = clock64()
+#define PROF_END(i) pacc[i] += clock64() - pt0
+#define PROF_STAMP(i) pacc[i] = clock64() - pstart
+#define PROF_FLUSH                                                        \
+  if (lane == 0 && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 0) \
+    for (int i_ = 0; i_ < 8; ++i_) g_attn_prof[warp][i_] = pacc[i_]
+#else
+#define PROF_DECL
+#define PROF_BEGIN
+#define PROF_END(i)
+#define PROF_STAMP(i)
+#define PROF_FLUSH
+#endif
+// tcgen05.ld 32x32b.x32 straight into a slice of a float array (the instruction is .b32-typed)
+__device__ __forceinline__ void tmem_ld_x32f(uint32_t taddr, float (&r)[64], int o) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(r[o + 0]), "=f"(r[o + 1]), "=f"(r[o + 2]), "=f"(r[o + 3]), "=f"(r[o + 4]), "=f"(r[o + 5]),
+        "=f"(r[o + 6]), "=f"(r[o + 7]), "=f"(r[o + 8]), "=f"(r[o + 9]), "=f"(r[o + 10]), "=f"(r[o + 11]),
+        "=f"(r[o + 12]), "=f"(r[o + 13]), "=f"(r[o + 14]), "=f"(r[o + 15]), "=f"(r[o + 16]), "=f"(r[o + 17]),
+        "=f"(r[o + 18]), "=f"(r[o + 19]), "=f"(r[o + 20]), "=f"(r[o + 21]), "=f"(r[o + 22]), "=f"(r[o + 23]),
+        "=f"(r[o + 24]), "=f"(r[o + 25]), "=f"(r[o + 26]), "=f"(r[o + 27]), "=f"(r[o + 28]), "=f"(r[o + 29]),
+        "=f"(r[o + 30]), "=f"(r[o + 31])
+      : "r"(taddr)
+      : "memory");
+}
+constexpr int kGlobThreads = 384;   // warps 0-3 / 4-7: softmax warpgroups, 8: TMA + TMEM alloc, 9: MMA, 10-11 idle
+
+template <int HD>
+struct GCfg {
+  static constexpr int E = 64, S = E * E, kQTiles = S / 128, kKVTiles = S / 128;
+  static constexpr int kTail = HD - 64;                      // 0 or 16
+  static constexpr int kMainBytes = 128 * 128;               // 128 rows x 64 fp16, 128B swizzle
+  static constexpr int kTailBytes = kTail ? 128 * 32 : 0;    // 128 rows x 16 fp16, 32B swizzle
+  static constexpr int kTileBytes = kMainBytes + kTailBytes; // Q / K / V tile and one rel-pos table
+  static constexpr int kSlots = 3;
+  // shared memory carve (all tile bases 1024-aligned)
+  static constexpr int oQ = 0;
+  static constexpr int oRp = oQ + kTileBytes;                // Rph | Rpw, then K slot 2 | V slot 2
+  static constexpr int oK = oRp + 2 * kTileBytes;            // K slots 0, 1
+  static constexpr int oV = oK + 2 * kTileBytes;             // V slots 0, 1
+  static constexpr int oBh = oV + 2 * kTileBytes;            // float [64 key rows][128 queries]
+  static constexpr int oBw = oBh + 64 * 128 * 4;             // float [128 queries][64 key cols], swizzled
+  static constexpr int oX = oBw + 128 * 64 * 4;              // float xmax[2][2][128], xsum[2][128]
+  static constexpr int oBars = oX + 6 * 128 * 4;
+  static constexpr int kNumBars = 1 + 4 * kSlots + 2 + 3 + 3 + 2;
+  static constexpr int kSmemBytes = oBars + kNumBars * 8 + 16 + 1024;
+  static constexpr int cO = 384;                             // TMEM: S buffers at 0 / 128 / 256, O at 384
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kGlobThreads, 1)
+attn_glob_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid_constant__ CUtensorMap map_qkv_tail,
+                 const __grid_constant__ CUtensorMap map_rph_main, const __grid_constant__ CUtensorMap map_rph_tail,
+                 const __grid_constant__ CUtensorMap map_rpw_main, const __grid_constant__ CUtensorMap map_rpw_tail,
+                 __half* __restrict__ out, int heads, float scale, int relw_mode) {
+  using C = GCfg<HD>;
+  constexpr int E = C::E, S = C::S, T = C::kKVTiles;
+  PROF_DECL;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem + C::oQ;
+  uint8_t* sRph = smem + C::oRp;
+  uint8_t* sRpw = sRph + C::kTileBytes;
+  float* sBh = reinterpret_cast<float*>(smem + C::oBh);
+  float* sBw = reinterpret_cast<float*>(smem + C::oBw);
+  float* sX = reinterpret_cast<float*>(smem + C::oX);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBars);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + 3;
+  uint64_t* v_full = k_empty + 3;
+  uint64_t* v_empty = v_full + 3;
+  uint64_t* t_full = v_empty + 3;
+  uint64_t* t_done = t_full + 1;
+  uint64_t* s_full = t_done + 1;
+  uint64_t* p_full = s_full + 3;
+  uint64_t* pv_done = p_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  auto k_slot = [&](int i) -> uint8_t* { return i < 2 ? smem + C::oK + i * C::kTileBytes : sRph; };
+  auto v_slot = [&](int i) -> uint8_t* { return i < 2 ? smem + C::oV + i * C::kTileBytes : sRpw; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int D = heads * HD;
+  const int m0 = q_tile * 128;
+
+  if (warp == 9 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_done, 8);
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // 384 threads start with 168 registers each; the softmax warpgroups need ~220 (64 scores + 64
+  // prefetched scores + 32 packed probabilities), the third warpgroup needs almost none
+  // (each setmaxnreg sits at the top of its role branch: ptxas budgets registers per branch)
+  if (warp == 8) {
+    reg_dealloc<72>();
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 3 * C::kTileBytes);
+      tma_load_3d(sQ, &map_qkv_main, q_full, head * HD, m0, b);
+      tma_load_2d(sRph, &map_rph_main, q_full, 0, 0);
+      tma_load_2d(sRpw, &map_rpw_main, q_full, 0, 0);
+      if (C::kTail) {
+        tma_load_3d(sQ + C::kMainBytes, &map_qkv_tail, q_full, head * HD + 64, m0, b);
+        tma_load_2d(sRph + C::kMainBytes, &map_rph_tail, q_full, 64, 0);
+        tma_load_2d(sRpw + C::kMainBytes, &map_rpw_tail, q_full, 64, 0);
+      }
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < T; ++j) {
+        if (j == 2) mbar_wait(t_full, 0);     // slot 2 aliases the rel-pos tables
+        uint8_t* sK = k_slot(slot);
+        uint8_t* sV = v_slot(slot);
+        PROF_BEGIN;
+        mbar_wait(&k_empty[slot], ph ^ 1);
+        PROF_END(0);
+        mbar_arrive_expect_tx(&k_full[slot], C::kTileBytes);
+        tma_load_3d(sK, &map_qkv_main, &k_full[slot], D + head * HD, j * 128, b);
+        if (C::kTail) tma_load_3d(sK + C::kMainBytes, &map_qkv_tail, &k_full[slot], D + head * HD + 64, j * 128, b);
+        PROF_BEGIN;
+        mbar_wait(&v_empty[slot], ph ^ 1);
+        PROF_END(1);
+        mbar_arrive_expect_tx(&v_full[slot], C::kTileBytes);
+        tma_load_3d(sV, &map_qkv_main, &v_full[slot], 2 * D + head * HD, j * 128, b);
+        if (C::kTail)
+          tma_load_3d(sV + C::kMainBytes, &map_qkv_tail, &v_full[slot], 2 * D + head * HD + 64, j * 128, b);
+        if (++slot == 3) { slot = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    reg_dealloc<72>();
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0);
+    constexpr uint32_t idesc_pv_main = make_idesc_f16(128, 64, 1);
+    constexpr uint32_t idesc_pv_tail = make_idesc_f16(128, 16, 1);
+    const uint64_t q_main = make_smem_desc(smem_u32(sQ), 0, 1024, kLayoutSw128);
+    const uint64_t q_tail = make_smem_desc(smem_u32(sQ + C::kMainBytes), 0, 256, kLayoutSw32);
+    // D[128 queries, 128] = Q . B^T for a K-major 128-row tile B (K tile or rel-pos table)
+    auto mma_q_times = [&](uint32_t d_tmem, const uint8_t* tile, uint64_t* bar0, uint64_t* bar1) {
+      const uint64_t b_main = make_smem_desc(smem_u32(tile), 0, 1024, kLayoutSw128);
+      const uint64_t b_tail = make_smem_desc(smem_u32(tile + C::kMainBytes), 0, 256, kLayoutSw32);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc_qk, k > 0);
+        if (C::kTail) tc_mma_ss(d_tmem, q_tail, b_tail, idesc_qk, 1);
+        if (bar0) tc_commit(bar0);
+        if (bar1) tc_commit(bar1);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    mma_q_times(tmem_base + 0, sRph, nullptr, nullptr);
+    mma_q_times(tmem_base + 128, sRpw, t_full, nullptr);
+    mbar_wait(t_done, 0);                      // T_h / T_w have been copied out of TMEM
+    tc_fence_after();
+    for (int i = 0; i < 2; ++i) {
+      mbar_wait(&k_full[i], 0);
+      tc_fence_after();
+      mma_q_times(tmem_base + 128 * i, k_slot(i), &s_full[i], &k_empty[i]);
+    }
+    int slot = 0, slot2 = 2;                   // slot of tile j / tile j + 2
+    uint32_t ph = 0, ph2 = 0;
+    for (int j = 0; j < T; ++j) {
+      if (j + 2 < T) {
+        PROF_BEGIN;
+        mbar_wait(&k_full[slot2], ph2);
+        PROF_END(0);
+        tc_fence_after();
+        mma_q_times(tmem_base + 128 * slot2, k_slot(slot2), &s_full[slot2], &k_empty[slot2]);
+      }
+      PROF_BEGIN;
+      mbar_wait(&p_full[slot], ph);
+      PROF_END(1);
+      PROF_BEGIN;
+      mbar_wait(&v_full[slot], ph);
+      PROF_END(2);
+      tc_fence_after();
+      const uint8_t* sV = v_slot(slot);
+      const uint32_t p_tmem = tmem_base + 128 * slot;
+      const uint64_t v_main0 = make_smem_desc(smem_u32(sV), C::kMainBytes, 1024, kLayoutSw128);
+      const uint64_t v_tail0 = make_smem_desc(smem_u32(sV + C::kMainBytes), C::kTailBytes, 256, kLayoutSw32);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          tc_mma_ts(tmem_base + C::cO, p_tmem + ks * 8, v_main0 + (ks * 2048 >> 4), idesc_pv_main, acc);
+          if (C::kTail)
+            tc_mma_ts(tmem_base + C::cO + 64, p_tmem + ks * 8, v_tail0 + (ks * 512 >> 4), idesc_pv_tail, acc);
+        }
+        tc_commit(&v_empty[slot]);
+        tc_commit(&pv_done[j & 1]);
+      }
+      __syncwarp();
+      if (++slot == 3) { slot = 0; ph ^= 1; }
+      if (++slot2 == 3) { slot2 = 0; ph2 ^= 1; }
+    }
+  } else if (warp >= 10) {
+    reg_dealloc<72>();
+  } else {
+    reg_alloc<216>();
+    // ============================ softmax warpgroups ============================
+    const int g = warp >> 2;                  // 0: key row 2j, 1: key row 2j+1
+    const int e = warp & 3;                   // TMEM lane quadrant
+    const int row = e * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(e * 32) << 16;
+    const int m = m0 + row;
+    const int mh = m / E, mw = m % E;
+    const int swz = row & 7;                  // XOR swizzle of this row's 16-byte bw chunks
+
+    // ---- bias tables, TMEM -> shared (rounded through fp16 like the reference's fp16 rel-pos
+    // products): warpgroup 0 writes bh[kh][row] = T_h[row][mh - kh + 63], warpgroup 1 writes
+    // bw[row][kw] = T_w[row][rw - kw + 63], both pre-multiplied by log2(e) ----
+    PROF_STAMP(3);
+    mbar_wait(t_full, 0);
+    PROF_STAMP(4);
+    tc_fence_after();
+    {
+      const int rw = (relw_mode == SAMQ_RELW_UPSTREAM) ? mw : mh;
+      const uint32_t src = tmem_base + 128 * g + lane_off;
+      auto put = [&](int kidx, float t) {
+        const float v = kLog2e * __half2float(__float2half_rn(t));
+        if (g == 0) sBh[kidx * 128 + row] = v;
+        else sBw[row * 64 + ((((kidx >> 2) ^ swz) << 2) | (kidx & 3))] = v;
+      };
+      if (g == 0 || relw_mode != SAMQ_RELW_UPSTREAM) {
+        // the 64-entry window starts at column mh for every row of the warp (32 | 64): entry
+        // kidx = 63 - i sits in column mh + i, a compile-time register index
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(src + mh + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) put(63 - (c * 32 + i), __uint_as_float(r[i]));
+        }
+      } else {
+        // upstream rel_w semantics: the window start mw differs per row -> predicated scatter
+        const int base = rw + E - 1;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(src + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kidx = base - (c * 32 + i);
+            if (static_cast<unsigned>(kidx) < static_cast<unsigned>(E)) put(kidx, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t_done);
+    named_bar_sync(1, 256);                   // both tables visible to both warpgroups
+    // 16-byte chunk q of this row's bw lives at bw_addr ^ (q << 4) (+128 for the second half)
+    uint32_t bw_addr = smem_u32(sBw + row * 64) | (static_cast<uint32_t>(swz) << 4);
+    float c_scale = scale * kLog2e;
+    // opaque moves: without them ptxas re-derives both values from scratch at every use
+    asm volatile("mov.b32 %0, %0;" : "+r"(bw_addr));
+    asm volatile("mov.b32 %0, %0;" : "+f"(c_scale));
+    auto ld_bw = [&](int q, int hf) -> float4 {
+      float4 w;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                   : "r"((bw_addr ^ (q << 4)) + hf * 128));
+      return w;
+    };
+
+    // shared-memory scalars through explicit ld/st.shared (pointers captured by the lambdas below
+    // would otherwise degrade to generic loads)
+    const uint32_t bh_addr = smem_u32(sBh + g * 128 + row);            // + tile * 1024 bytes
+    const uint32_t x_mine = smem_u32(sX + g * 128 + row), x_other = smem_u32(sX + (1 - g) * 128 + row);
+    auto lds = [](uint32_t addr) -> float {
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+      return v;
+    };
+    auto sts = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
+
+    // Two score arrays alternate between "current tile" (scaled + column-biased scores x) and
+    // "prefetched next tile" (raw S from TMEM, turned into x in place).
+    float xa[64], xb[64];
+    float mx_raw;
+    auto fetch = [&](float (&r)[64], int buf) {
+      const uint32_t s_tmem = tmem_base + 128 * buf + lane_off + 64 * g;
+      tmem_ld_x32f(s_tmem, r, 0);
+      tmem_ld_x32f(s_tmem + 32, r, 32);
+    };
+    // r <- r * scale*log2e + bw (this thread's 64 key columns); returns the maximum
+    auto bias_max = [&](float (&r)[64]) -> float {
+      float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int o = 32 * hf + 4 * q;
+          const float4 w = ld_bw(q, hf);
+          r[o + 0] = fmaf(r[o + 0], c_scale, w.x);
+          r[o + 1] = fmaf(r[o + 1], c_scale, w.y);
+          r[o + 2] = fmaf(r[o + 2], c_scale, w.z);
+          r[o + 3] = fmaf(r[o + 3], c_scale, w.w);
+          a0 = fmaxf(a0, fmaxf(r[o + 0], r[o + 2]));
+          a1 = fmaxf(a1, fmaxf(r[o + 1], r[o + 3]));
+        }
+      }
+      return fmaxf(a0, a1);
+    };
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    fetch(xa, 0);
+    tmem_ld_wait();
+    mx_raw = bias_max(xa);
+    PROF_STAMP(5);
+
+    float m_used = -INFINITY, l = 0.f;
+    constexpr uint32_t o_cols = HD / 2;       // O columns rescaled / stored by this warpgroup
+    int buf = 0, nbuf = 1;                    // S buffer of tile j / tile j + 1
+    uint32_t nph = 0;                         // parity of s_full[nbuf] for tile j + 1
+    int j = 0;
+    // One key tile: x = scores of tile j, nx = landing zone of tile j + 1.  `more` = a next tile
+    // exists (the last tile is peeled, so each body is branch-free and can be scheduled freely).
+    auto tile_step = [&](float (&x)[64], float (&nx)[64], auto more_tag) {
+      constexpr bool more = decltype(more_tag)::value;
+      const float bh = lds(bh_addr + j * 1024);
+      const float mx = mx_raw + bh;
+      const uint32_t xoff = (j & 1) * 1024;
+      sts(x_mine + xoff, mx);
+      // prefetch the next tile's scores; they land while the maxima are exchanged
+      if (more) {
+        PROF_BEGIN;
+        mbar_wait(&s_full[nbuf], nph);
+        PROF_END(0);
+        tc_fence_after();
+        fetch(nx, nbuf);
+      }
+      PROF_BEGIN;
+      named_bar_sync(1, 256);
+      PROF_END(1);
+      const float m_new = fmaxf(m_used, fmaxf(mx, lds(x_other + xoff)));
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, m_new > m_used + 8.f)) {
+        // lazy rescale; both warpgroups take the same decision (same data), each rescales its
+        // half of the O columns
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const float alpha = ex2(m_used - m_new);
+        l *= alpha;
+        m_used = m_new;
+        const uint32_t o_tmem = tmem_base + C::cO + lane_off + g * o_cols;
+        {
+          uint32_t r[32];
+          tmem_ld_x32(o_tmem, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x32(o_tmem, r);
+        }
+        if (HD == 80) {
+          uint32_t r[8];
+          tmem_ld_x8(o_tmem + 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x8(o_tmem + 32, r);
+        }
+        tmem_st_wait();
+      }
+      PROF_BEGIN;
+      if (more) tmem_ld_wait();
+      const float mm = m_used - bh;
+      // ---- P = 2^(x - m) -> P columns [32g, 32g + 32) of the tile's S buffer.  Warpgroup 1's P
+      // columns overlap warpgroup 0's S columns [32, 64): all S reads of this tile completed one
+      // iteration ago (prefetch), before the barrier above. ----
+      uint32_t pk[32];
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float p0 = ex2(x[i + 0] - mm), p1 = ex2(x[i + 1] - mm);
+        const float p2 = ex2(x[i + 2] - mm), p3 = ex2(x[i + 3] - mm);
+        sum0 += p0 + p2;
+        sum1 += p1 + p3;
+        pk[(i >> 1) + 0] = pack_h2(p0, p1);
+        pk[(i >> 1) + 1] = pack_h2(p2, p3);
+      }
+      l += sum0 + sum1;
+      tmem_st_x32(tmem_base + 128 * buf + lane_off + 32 * g, pk);
+      if (more) mx_raw = bias_max(nx);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[buf]);
+      PROF_END(2);
+      buf = nbuf;
+      if (++nbuf == 3) { nbuf = 0; nph ^= 1; }   // tile t lives in buffer t % 3, phase (t / 3) & 1
+      ++j;
+    };
+    for (int jj = 0; jj < T / 2 - 1; ++jj) {
+      tile_step(xa, xb, std::true_type{});
+      tile_step(xb, xa, std::true_type{});
+    }
+    tile_step(xa, xb, std::true_type{});
+    tile_step(xb, xa, std::false_type{});
+
+    PROF_STAMP(6);
+    // ---- epilogue: combine the two partial sums of each row, O / l ----
+    sts(x_mine + 2048, l);
+    named_bar_sync(1, 256);
+    const float inv_l = 1.f / (l + lds(x_other + 2048));
+    mbar_wait(&pv_done[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    tc_fence_after();
+    const uint32_t o_tmem = tmem_base + C::cO + lane_off + g * o_cols;
+    __half* dst = out + (static_cast<size_t>(b) * S + m) * D + head * HD + g * o_cols;
+    {
+      uint32_t r[32];
+      tmem_ld_x32(o_tmem, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint4 o;
+        o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+        o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+        o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+        o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + v * 8) = o;
+      }
+    }
+    if (HD == 80) {
+      uint32_t r[8];
+      tmem_ld_x8(o_tmem + 32, r);
+      tmem_ld_wait();
+      uint4 o;
+      o.x = pack_h2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+      o.y = pack_h2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+      o.z = pack_h2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+      o.w = pack_h2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+      *reinterpret_cast<uint4*>(dst + 32) = o;
+    }
+  }
+
+  PROF_STAMP(7);
+  PROF_FLUSH;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HD>
+int launch_attn_glob(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads, float scale,
+                     int relw_mode, cudaStream_t st) {
+  using C = GCfg<HD>;
+  const int D = heads * HD;
+  const uint64_t row_bytes = static_cast<uint64_t>(3) * D * 2;
+  uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {row_bytes, row_bytes * C::S};
+  uint32_t box_main[3] = {64, 128, 1}, box_tail[3] = {16, 128, 1};
+  const CUtensorMap* m_main = get_tensor_map_nd(qkv, 3, dims, strides, box_main, 2, 3);
+  const int rp_rows = 2 * C::E - 1;
+  const CUtensorMap* h_main = get_tensor_map_2d(rph, rp_rows, HD, HD * 2, 128, 64, 2, 3);
+  const CUtensorMap* w_main = get_tensor_map_2d(rpw, rp_rows, HD, HD * 2, 128, 64, 2, 3);
+  if (!m_main || !h_main || !w_main) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap *m_tail = m_main, *h_tail = h_main, *w_tail = w_main;
+  if (C::kTail) {
+    m_tail = get_tensor_map_nd(qkv, 3, dims, strides, box_tail, 2, 1);
+    h_tail = get_tensor_map_2d(rph, rp_rows, HD, HD * 2, 128, 16, 2, 1);
+    w_tail = get_tensor_map_2d(rpw, rp_rows, HD, HD * 2, 128, 16, 2, 1);
+    if (!m_tail || !h_tail || !w_tail) return SAMQ_ERR_LAUNCH;
+  }
+  auto kern = attn_glob_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_glob smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
+      return SAMQ_ERR_LAUNCH;
+    }
+    attr_set = true;
+  }
+  dim3 grid(C::kQTiles, heads, B);
+  kern<<<grid, kGlobThreads, C::kSmemBytes, st>>>(*m_main, *m_tail, *h_main, *h_tail, *w_main, *w_tail,
+                                                 reinterpret_cast<__half*>(out), heads, scale, relw_mode);
+  count_launch();
+  return check_launch("attn_glob_kernel");
+}
+
 template <int HD, bool WIN>
 int launch_attn(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads,
                 float scale, int relw_mode, cudaStream_t st) {
@@ -826,6 +1366,12 @@ extern "C" int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, cons
                "samq_attn_relpos_fwd: (H,W)=(%d,%d) not supported ((64,64) or (14,14))", H, W);
   const char* wv = getenv("SAMQ_ATTN_WIN");   // "v1": first windowed design (two key tiles), ablation only
   const bool win_v1 = wv && strcmp(wv, "v1") == 0;
+  const char* gv = getenv("SAMQ_ATTN_GLOB");  // "v1": first global design (one softmax warpgroup)
+  const bool glob_v1 = gv && strcmp(gv, "v1") == 0;
+  if (glob && !glob_v1) {
+    return hd == 64 ? launch_attn_glob<64>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
+                    : launch_attn_glob<80>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+  }
   if (hd == 64) {
     if (glob) return launch_attn<64, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
     return win_v1 ? launch_attn<64, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
