@@ -432,6 +432,27 @@ attn_relpos_kernel(const __grid_constant__ CUtensorMap map_qkv_main,
   }
 }
 
+#ifdef SAMQ_ATTN_PROFILE
+// developer-only wait-time breakdown (tests/micro/attn_prof.cu); never compiled into libsamq.so
+__device__ long long g_attn_prof[12][8];
+#define PROF_DECL long long pt0 = 0, pstart = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_BEGIN pt0 = clock64()
+#ifdef SAMQ_ATTN_STAMPS
+#define PROF_END(i)
+#else
+#define PROF_END(i) pacc[i] += clock64() - pt0
+#endif
+#define PROF_STAMP(i) pacc[i] = clock64() - pstart
+#define PROF_FLUSH                                                        \
+  if (lane == 0 && blockIdx.x == (gridDim.x > 3 ? 3 : 0) && blockIdx.y == (gridDim.y > 1 ? 1 : 0) && blockIdx.z == 0) \
+    for (int i_ = 0; i_ < 8; ++i_) g_attn_prof[warp][i_] = pacc[i_]
+#else
+#define PROF_DECL
+#define PROF_BEGIN
+#define PROF_END(i)
+#define PROF_STAMP(i)
+#define PROF_FLUSH
+#endif
 // ===========================================================================================
 // Windowed attention, second design: the whole 14x14 window (196 keys, padded to 208) is ONE
 // key tile, so the softmax is exact single-pass (no online rescaling), and the CTA is small
@@ -475,6 +496,7 @@ attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_con
                 __half* __restrict__ out, int heads, float scale, int relw_mode) {
   using C = WCfg<HD>;
   constexpr int E = C::E, S = C::S, SP = C::SP;
+  PROF_DECL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -589,7 +611,9 @@ attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_con
     const int mh = valid ? m / E : 0, mw = valid ? m % E : 0;
     const float c_scale = scale * kLog2e;
 
+    PROF_STAMP(0);
     mbar_wait(t_full, 0);
+    PROF_STAMP(1);
     tc_fence_after();
     uint32_t* my_th = sTh + row * C::kBounceWords;
     uint32_t* my_tw = sTw + row * C::kBounceWords;
@@ -620,8 +644,10 @@ attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_con
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(b_done);
+    PROF_STAMP(2);
 
     mbar_wait(s_full, 0);
+    PROF_STAMP(3);
     tc_fence_after();
     const uint32_t s_tmem = tmem_base + C::cS + lane_off;
     float l = 0.f;
@@ -638,6 +664,7 @@ attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_con
         for (int j = 0; j < 28; ++j)
           mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), c_scale, bw[j % E]) + bh[2 * i + (j >= E ? 1 : 0)]);
       }
+      PROF_STAMP(4);
       // (the bias is added as fma(s, c, bw) + bh so that nothing but the 28 table values is
       // loop-invariant: summing bh + bw first made the compiler keep 196 sums alive and spill)
 #pragma unroll
@@ -670,9 +697,11 @@ attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_con
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(p_full);
+    PROF_STAMP(5);
 
     // ---- epilogue: O / l ----
     mbar_wait(o_full, 0);
+    PROF_STAMP(6);
     tc_fence_after();
     if (warp_valid) {
       const float inv_l = 1.f / l;
@@ -714,6 +743,8 @@ attn_win_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_con
     }
   }
 
+  PROF_STAMP(7);
+  PROF_FLUSH;
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -763,6 +794,509 @@ int launch_attn_win(const void* qkv, const void* rph, const void* rpw, void* out
 }
 
 // ===========================================================================================
+// Windowed attention, third design: PERSISTENT CTAs, one per SM, streaming (window, head) items.
+//
+// Timeline of the second design (clock64 stamps, tests/micro/attn_prof.cu): per CTA 0.9k clk
+// set-up, 3.0k waiting for the first TMA + rel-pos MMAs, 1.0k bias bounce, 1.4k max pass, 3.7k
+// exp pass, 1.6k PV, 2.4k epilogue = 14.5k clk, two CTAs per window-head (K / V loaded twice),
+// two CTAs per SM: 14.5k clk per item per SM against a MUFU floor of 3.1k.  Here:
+//   * a CTA loops over items; the TMA warp runs up to two items ahead (Q, K, V rings of 2), so
+//     load latency and set-up are paid once per CTA, and K / V are loaded once per item;
+//   * the item's two 128-query tiles (rows 0-127 / 128-195) are two INDEPENDENT pipelines, each a
+//     softmax warpgroup plus its own MMA-issuing warp and its own 208-column TMEM region:
+//       T = Q.[Rph;Rpw]^T -> bias registers -> S = Q.K^T -> max pass -> exp pass (P over S)
+//       -> O = P.V (columns 112..191 of the region) -> O/l -> shared -> TMA store;
+//     while one pipeline waits for its MMAs the other one computes;
+//   * the bias values are picked straight out of TMEM: all rows of a warp span at most four image
+//     rows mh, and T_h[row][mh + 13 - kh] is a 14-column window starting at column mh, so one
+//     x16 load per distinct mh plus a predicated move replaces the shared-memory bounce;
+//   * O is staged in the (dead) Q slot in the TMA swizzle layouts and written with a TMA store,
+//     which also clips the rows beyond token 195.
+// ===========================================================================================
+constexpr int kWin3Threads = 384;   // warps 0-3 / 4-7: softmax WG of tile A / B, 8: TMA, 9 / 10: MMA of tile A / B
+
+template <int HD>
+struct W3Cfg {
+  static constexpr int E = 14, S = 196, SP = 208;
+  static constexpr int kTail = HD - 64;
+  static constexpr int kRowsB = 80;                                   // tile B: tokens 128..195 (+ zero rows)
+  static constexpr int kQAMain = 128 * 128, kQBMain = kRowsB * 128;
+  static constexpr int kQATail = kTail ? 128 * 32 : 0, kQBTail = kTail ? kRowsB * 32 : 0;
+  static constexpr int oQA = 0, oQB = oQA + kQAMain, oQAT = oQB + kQBMain, oQBT = oQAT + kQATail;
+  static constexpr int kQStage = ((oQBT + kQBTail + 1023) / 1024) * 1024;
+  static constexpr int kKVMain = SP * 128, kKVTail = kTail ? SP * 32 : 0;
+  static constexpr int oKM = 0, oVM = kKVMain, oKT = 2 * kKVMain, oVT = oKT + kKVTail;
+  static constexpr int kKVStage = ((oVT + kKVTail + 1023) / 1024) * 1024;
+  static constexpr int kRpMain = 32 * 128, kRpTail = kTail ? 32 * 32 : 0;
+  // [Rph main | Rpw main | Rph tail | Rpw tail]: the two tables form one 64-row B operand
+  static constexpr int oRp = 0;
+  static constexpr int kRpBytes = ((2 * kRpMain + 2 * kRpTail + 1023) / 1024) * 1024;
+  static constexpr int oQ = oRp + kRpBytes;
+  static constexpr int oKV = oQ + 2 * kQStage;
+  static constexpr int oL = oKV + 2 * kKVStage;
+  static constexpr int oBars = oL;
+  static constexpr int kNumBars = 1 + 6 * 2 + 6 * 2;
+  static constexpr int kSmemBytes = oBars + kNumBars * 8 + 16 + 1024;
+  static constexpr int cO = 112;                                      // O columns inside a region
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kWin3Threads, 1)
+attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_constant__ CUtensorMap map_qa_tail,
+                 const __grid_constant__ CUtensorMap map_qb_main, const __grid_constant__ CUtensorMap map_qb_tail,
+                 const __grid_constant__ CUtensorMap map_kv_main, const __grid_constant__ CUtensorMap map_kv_tail,
+                 const __grid_constant__ CUtensorMap map_rph_main, const __grid_constant__ CUtensorMap map_rph_tail,
+                 const __grid_constant__ CUtensorMap map_rpw_main, const __grid_constant__ CUtensorMap map_rpw_tail,
+                 const __grid_constant__ CUtensorMap map_o_main, const __grid_constant__ CUtensorMap map_o_tail,
+                 int heads, int n_items, float scale, int relw_mode) {
+  using C = W3Cfg<HD>;
+  constexpr int E = C::E, S = C::S, SP = C::SP;
+  PROF_DECL;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sRp = smem + C::oRp;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::oBars);
+  uint64_t* rp_full = bars;
+  uint64_t* q_full = bars + 1;       // [2 stages]
+  uint64_t* q_empty = q_full + 2;    // count 2: both tiles' O stores have read the slot
+  uint64_t* k_full = q_empty + 2;
+  uint64_t* k_empty = k_full + 2;    // count 2: both tiles' QK^T retired
+  uint64_t* v_full = k_empty + 2;
+  uint64_t* v_empty = v_full + 2;    // count 2: both tiles' PV retired
+  uint64_t* t_full = v_empty + 2;    // [2 tiles] from here on
+  uint64_t* t_done = t_full + 2;     // count 4
+  uint64_t* s_full = t_done + 2;
+  uint64_t* p_full = s_full + 2;     // count 4
+  uint64_t* o_full = p_full + 2;
+  uint64_t* o_free = o_full + 2;     // count 4: O has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = heads * HD;
+
+  if (warp == 9 && lane == 0) {
+    mbar_init(rp_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2);
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
+      mbar_init(&t_full[i], 1); mbar_init(&t_done[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(rp_full, 2 * (C::kRpMain + C::kRpTail));
+      tma_load_2d(sRp, &map_rph_main, rp_full, 0, 0);
+      tma_load_2d(sRp + C::kRpMain, &map_rpw_main, rp_full, 0, 0);
+      if (C::kTail) {
+        tma_load_2d(sRp + 2 * C::kRpMain, &map_rph_tail, rp_full, 64, 0);
+        tma_load_2d(sRp + 2 * C::kRpMain + C::kRpTail, &map_rpw_tail, rp_full, 64, 0);
+      }
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int st = n & 1;
+        const uint32_t ph = (n >> 1) & 1;
+        const int b = item / heads, head = item % heads;
+        uint8_t* sQ = smem + C::oQ + st * C::kQStage;
+        uint8_t* sKV = smem + C::oKV + st * C::kKVStage;
+        mbar_wait(&q_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&q_full[st], C::kQAMain + C::kQBMain + C::kQATail + C::kQBTail);
+        tma_load_3d(sQ + C::oQA, &map_qa_main, &q_full[st], head * HD, 0, b);
+        tma_load_3d(sQ + C::oQB, &map_qb_main, &q_full[st], head * HD, 128, b);
+        if (C::kTail) {
+          tma_load_3d(sQ + C::oQAT, &map_qa_tail, &q_full[st], head * HD + 64, 0, b);
+          tma_load_3d(sQ + C::oQBT, &map_qb_tail, &q_full[st], head * HD + 64, 128, b);
+        }
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], C::kKVMain + C::kKVTail);
+        tma_load_3d(sKV + C::oKM, &map_kv_main, &k_full[st], D + head * HD, 0, b);
+        if (C::kTail) tma_load_3d(sKV + C::oKT, &map_kv_tail, &k_full[st], D + head * HD + 64, 0, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], C::kKVMain + C::kKVTail);
+        tma_load_3d(sKV + C::oVM, &map_kv_main, &v_full[st], 2 * D + head * HD, 0, b);
+        if (C::kTail) tma_load_3d(sKV + C::oVT, &map_kv_tail, &v_full[st], 2 * D + head * HD + 64, 0, b);
+      }
+    }
+  } else if (warp == 9 || warp == 10) {
+    // ============================ MMA issuer of tile X ============================
+    const int X = warp - 9;
+    const uint32_t region = tmem_base + X * SP;
+    constexpr uint32_t idesc_t = make_idesc_f16(128, 64, 0);
+    constexpr uint32_t idesc_qk = make_idesc_f16(128, SP, 0);
+    constexpr uint32_t idesc_pv_main = make_idesc_f16(128, 64, 1);
+    constexpr uint32_t idesc_pv_tail = make_idesc_f16(128, 16, 1);
+    const uint64_t rp_main = make_smem_desc(smem_u32(sRp), 0, 1024, kLayoutSw128);
+    const uint64_t rp_tail = make_smem_desc(smem_u32(sRp + 2 * C::kRpMain), 0, 256, kLayoutSw32);
+    mbar_wait(rp_full, 0);
+    int n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const int st = n & 1;
+      const uint32_t ph = (n >> 1) & 1, pn = n & 1;
+      const uint8_t* sQ = smem + C::oQ + st * C::kQStage;
+      const uint8_t* sKV = smem + C::oKV + st * C::kKVStage;
+      const uint64_t q_main = make_smem_desc(smem_u32(sQ + (X ? C::oQB : C::oQA)), 0, 1024, kLayoutSw128);
+      const uint64_t q_tail = make_smem_desc(smem_u32(sQ + (X ? C::oQBT : C::oQAT)), 0, 256, kLayoutSw32);
+      // D[128, N] = Q . B^T for a K-major B tile (rel-pos tables or K)
+      auto mma_q_times = [&](uint64_t b_main, uint64_t b_tail, uint32_t idesc, uint64_t* bar0, uint64_t* bar1) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_ss(region, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc, k > 0);
+          if (C::kTail) tc_mma_ss(region, q_tail, b_tail, idesc, 1);
+          tc_commit(bar0);
+          if (bar1) tc_commit(bar1);
+        }
+        __syncwarp();
+      };
+      // rel-pos tables into columns [0, 64) of the region (free once the previous O was read)
+      PROF_BEGIN;
+      mbar_wait(&q_full[st], ph);
+      PROF_END(0);
+      PROF_BEGIN;
+      mbar_wait(&o_free[X], pn ^ 1);
+      PROF_END(1);
+      tc_fence_after();
+      mma_q_times(rp_main, rp_tail, idesc_t, &t_full[X], nullptr);
+#ifdef SAMQ_ATTN_PROFILE
+      PROF_BEGIN;
+      mbar_wait(&t_full[X], pn);
+      PROF_END(2);
+#endif
+      // S = Q K^T over the whole region once the bias values have been read out
+      PROF_BEGIN;
+      mbar_wait(&k_full[st], ph);
+      mbar_wait(&t_done[X], pn);
+      PROF_END(3);
+      tc_fence_after();
+      mma_q_times(make_smem_desc(smem_u32(sKV + C::oKM), 0, 1024, kLayoutSw128),
+                  make_smem_desc(smem_u32(sKV + C::oKT), 0, 256, kLayoutSw32), idesc_qk, &s_full[X], &k_empty[st]);
+#ifdef SAMQ_ATTN_PROFILE
+      PROF_BEGIN;
+      mbar_wait(&s_full[X], pn);
+      PROF_END(4);
+#endif
+      // O = P V
+      PROF_BEGIN;
+      mbar_wait(&v_full[st], ph);
+      mbar_wait(&p_full[X], pn);
+      PROF_END(5);
+      tc_fence_after();
+      const uint64_t v_main0 = make_smem_desc(smem_u32(sKV + C::oVM), C::kKVMain, 1024, kLayoutSw128);
+      const uint64_t v_tail0 = make_smem_desc(smem_u32(sKV + C::oVT), 4096, 256, kLayoutSw32);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < SP / 16; ++ks) {
+          tc_mma_ts(region + C::cO, region + ks * 8, v_main0 + (ks * 2048 >> 4), idesc_pv_main, ks > 0);
+          if (C::kTail)
+            tc_mma_ts(region + C::cO + 64, region + ks * 8, v_tail0 + (ks * 512 >> 4), idesc_pv_tail, ks > 0);
+        }
+        tc_commit(&o_full[X]);
+        tc_commit(&v_empty[st]);
+      }
+      __syncwarp();
+#ifdef SAMQ_ATTN_PROFILE
+      PROF_BEGIN;
+      mbar_wait(&o_full[X], pn);
+      PROF_END(6);
+#endif
+    }
+  } else if (warp < 8) {
+    // ============================ softmax warpgroup of tile X ============================
+    const int X = warp >> 2;
+    const int e = warp & 3;
+    const int row = e * 32 + lane;                    // row of the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(e * 32) << 16;
+    const uint32_t region = tmem_base + X * SP + lane_off;
+    const int m = X * 128 + row;                      // token inside the window
+    const bool valid = m < S;
+    const bool warp_valid = (X * 128 + e * 32) < S;   // warp-uniform: any valid row in this warp
+    const int mh = valid ? m / E : 0, mw = valid ? m % E : 0;
+    // distinct table windows needed by this warp: image rows of its first / last valid token
+    const int m_first = X * 128 + e * 32, m_last = min(m_first + 31, S - 1);
+    const int vh_lo = m_first / E, vh_hi = m_last / E;
+    float c_scale = scale * kLog2e;
+    asm volatile("mov.b32 %0, %0;" : "+f"(c_scale));
+    // this row's O staging addresses inside the Q slot (same swizzles as the TMA tiles)
+    const uint32_t o_main_off = (X ? C::oQB : C::oQA) + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t o_tail_off = (X ? C::oQBT : C::oQAT) + (row >> 3) * 256 + (row & 7) * 32;
+    const bool stage_row = X == 0 || row < C::kRowsB;
+
+    int n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const int st = n & 1;
+      const uint32_t pn = n & 1;
+      const int b = item / heads, head = item % heads;
+      uint8_t* sQ = smem + C::oQ + st * C::kQStage;
+
+      // ---- bias values out of TMEM: bh[k] = T_h[row][mh + 13 - k], bw[k] = T_w[row][rw + 13 - k],
+      // rounded through fp16 (the reference forms fp16 rel-pos products), times log2(e) ----
+      float bh[E], bw[E];
+#pragma unroll
+      for (int k = 0; k < E; ++k) bh[k] = bw[k] = 0.f;
+      PROF_BEGIN;
+      mbar_wait(&t_full[X], pn);
+      PROF_END(0);
+      PROF_BEGIN;
+      tc_fence_after();
+      if (warp_valid) {
+        if (relw_mode != SAMQ_RELW_UPSTREAM) {
+          // both tables are indexed by the image row: one pass over the warp's (<= 4) image rows
+          for (int v = vh_lo; v <= vh_hi; ++v) {
+            uint32_t rh[16], rv[16];
+            tmem_ld_x16(region + v, rh);
+            tmem_ld_x16(region + 32 + v, rv);
+            tmem_ld_wait();
+            if (mh == v) {
+#pragma unroll
+              for (int k = 0; k < E; ++k) {
+                bh[k] = __uint_as_float(rh[13 - k]);
+                bw[k] = __uint_as_float(rv[13 - k]);
+              }
+            }
+          }
+        } else {
+          for (int v = vh_lo; v <= vh_hi; ++v) {
+            uint32_t r[16];
+            tmem_ld_x16(region + v, r);
+            tmem_ld_wait();
+            if (mh == v) {
+#pragma unroll
+              for (int k = 0; k < E; ++k) bh[k] = __uint_as_float(r[13 - k]);
+            }
+          }
+          for (int v = 0; v < E; ++v) {
+            uint32_t r[16];
+            tmem_ld_x16(region + 32 + v, r);
+            tmem_ld_wait();
+            if (mw == v) {
+#pragma unroll
+              for (int k = 0; k < E; ++k) bw[k] = __uint_as_float(r[13 - k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          bh[k] = kLog2e * __half2float(__float2half_rn(bh[k]));
+          bw[k] = kLog2e * __half2float(__float2half_rn(bw[k]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_done[X]);
+      PROF_END(1);
+      PROF_BEGIN;
+
+      // ---- softmax over the 196 real keys: 7 steps of 2 key rows (28 keys) ----
+      // one-time half-period skew: tile B starts its first softmax when tile A has finished its
+      // first, so that afterwards one pipeline's exp pass (MUFU-bound) overlaps the other's
+      // MMA waits / max pass / epilogue instead of colliding with its exp pass
+      if (X == 1 && n == 0) mbar_wait(&p_full[0], 0);
+      mbar_wait(&s_full[X], pn);
+      PROF_END(2);
+      PROF_BEGIN;
+      tc_fence_after();
+      float l = 0.f;
+      if (warp_valid) {
+        // (the TMEM load of step i + 1 is in flight while step i is processed)
+        float mx = -INFINITY;
+        uint32_t ra[32], rb[32];
+        tmem_ld_x32(region, ra);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          uint32_t (&r)[32] = (i & 1) ? rb : ra;
+          tmem_ld_wait();
+          if (i < 6) tmem_ld_x32(region + 28 * (i + 1), (i & 1) ? ra : rb);
+          else tmem_ld_x32(region, rb);               // first step of the exp pass
+#pragma unroll
+          for (int j = 0; j < 28; ++j)
+            mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), c_scale, bw[j % E]) + bh[2 * i + (j >= E ? 1 : 0)]);
+        }
+        PROF_END(3);
+        PROF_BEGIN;
+#ifdef SAMQ_ATTN_STAMPS
+        if (n >= 5 && n <= 8) PROF_STAMP(2 * (n - 5));
+#endif
+        if (n > 0 && e == 0 && lane == 0) {
+          // the previous item's O store was queued ~2.5k clk ago: it has read its shared-memory
+          // source by now, so its Q slot can go back to the TMA producer
+          tma_store_wait_read<0>();
+          mbar_arrive(&q_empty[st ^ 1]);
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) bh[k] -= mx;
+        // P = 2^(x - max) as fp16 pairs, written behind the read pointer
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          uint32_t (&r)[32] = (i & 1) ? ra : rb;      // step 0 landed in rb
+          tmem_ld_wait();
+          if (i < 6) tmem_ld_x32(region + 28 * (i + 1), (i & 1) ? rb : ra);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 28; j += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[j]), c_scale, bw[j % E]) + bh[2 * i + (j >= E ? 1 : 0)]);
+            const float p1 =
+                ex2(fmaf(__uint_as_float(r[j + 1]), c_scale, bw[(j + 1) % E]) + bh[2 * i + (j + 1 >= E ? 1 : 0)]);
+            l += p0 + p1;
+            pk[j >> 1] = pack_h2(p0, p1);
+          }
+          pk[14] = 0;   // the two extra columns belong to the next step (rewritten there) or are
+          pk[15] = 0;   // the zero padding after key 195
+          // P columns [14i, 14i+16) lie behind both this step's and the prefetched step's S columns
+          tmem_st_x16(region + 14 * i, pk);
+        }
+        // padded keys 200..207 (P columns 100..103) must be exact zeros for the K = 208 PV MMA
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(region + 100), "r"(0u)
+                     : "memory");
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[X]);
+      PROF_END(4);
+      PROF_BEGIN;
+#ifdef SAMQ_ATTN_STAMPS
+      if (n >= 5 && n <= 8) PROF_STAMP(2 * (n - 5) + 1);
+#endif
+
+      // ---- O / l -> fp16 -> the item's Q slot (dead since S was formed) -> TMA store ----
+      mbar_wait(&o_full[X], pn);
+      PROF_END(5);
+      PROF_BEGIN;
+      tc_fence_after();
+      {
+        const float inv_l = warp_valid ? 1.f / l : 0.f;
+        const uint32_t o_tmem = region + C::cO;
+        const uint32_t swz = row & 7;
+        uint8_t* o_main = sQ + o_main_off;
+        uint8_t* o_tail = sQ + o_tail_off;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(o_tmem + c * 32, r);
+          tmem_ld_wait();
+          if (stage_row) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 o;
+              o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+              o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+              o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+              o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(o_main + (((c * 4 + v) ^ swz) << 4)) = o;
+            }
+          }
+        }
+        if (C::kTail) {
+          uint32_t r[16];
+          tmem_ld_x16(o_tmem + 64, r);
+          tmem_ld_wait();
+          if (stage_row) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              uint4 o;
+              o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
+              o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
+              o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
+              o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(o_tail + ((v ^ ((row >> 2) & 1)) << 4)) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[X]);         // the region may be overwritten
+      PROF_END(6);
+      PROF_BEGIN;
+      fence_proxy_async_smem();                       // staging writes -> visible to the TMA engine
+      named_bar_sync(1 + X, 128);
+      if (e == 0 && lane == 0) {
+        // queued without waiting; the slot is released during the next item (see the max pass)
+        tma_store_3d(&map_o_main, sQ + (X ? C::oQB : C::oQA), head * HD, X * 128, b);
+        if (C::kTail) tma_store_3d(&map_o_tail, sQ + (X ? C::oQBT : C::oQAT), head * HD + 64, X * 128, b);
+        tma_store_commit();
+      }
+      PROF_END(7);
+    }
+    if (e == 0 && lane == 0) tma_store_wait_all<0>();
+  }
+
+  PROF_FLUSH;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HD>
+int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads, float scale,
+                     int relw_mode, cudaStream_t st) {
+  using C = W3Cfg<HD>;
+  const int D = heads * HD;
+  const uint64_t row_bytes = static_cast<uint64_t>(3) * D * 2;
+  uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {row_bytes, row_bytes * C::S};
+  uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
+  uint64_t ostrides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(D) * 2 * C::S};
+  uint32_t qa_main[3] = {64, 128, 1}, qa_tail[3] = {16, 128, 1};
+  uint32_t qb_main[3] = {64, C::kRowsB, 1}, qb_tail[3] = {16, C::kRowsB, 1};
+  uint32_t kv_main[3] = {64, static_cast<uint32_t>(C::SP), 1}, kv_tail[3] = {16, static_cast<uint32_t>(C::SP), 1};
+  const CUtensorMap* mqa = get_tensor_map_nd(qkv, 3, dims, strides, qa_main, 2, 3);
+  const CUtensorMap* mqb = get_tensor_map_nd(qkv, 3, dims, strides, qb_main, 2, 3);
+  const CUtensorMap* mkv = get_tensor_map_nd(qkv, 3, dims, strides, kv_main, 2, 3);
+  const CUtensorMap* mh = get_tensor_map_2d(rph, 27, HD, HD * 2, 32, 64, 2, 3);
+  const CUtensorMap* mw = get_tensor_map_2d(rpw, 27, HD, HD * 2, 32, 64, 2, 3);
+  // O tiles are stored with the 128-row box for both tiles: tile B's rows 68.. are tokens >= 196
+  // and are clipped by the tensor bounds
+  const CUtensorMap* mo = get_tensor_map_nd(out, 3, odims, ostrides, qa_main, 2, 3);
+  if (!mqa || !mqb || !mkv || !mh || !mw || !mo) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap *mqat = mqa, *mqbt = mqb, *mkvt = mkv, *mht = mh, *mwt = mw, *mot = mo;
+  if (C::kTail) {
+    mqat = get_tensor_map_nd(qkv, 3, dims, strides, qa_tail, 2, 1);
+    mqbt = get_tensor_map_nd(qkv, 3, dims, strides, qb_tail, 2, 1);
+    mkvt = get_tensor_map_nd(qkv, 3, dims, strides, kv_tail, 2, 1);
+    mht = get_tensor_map_2d(rph, 27, HD, HD * 2, 32, 16, 2, 1);
+    mwt = get_tensor_map_2d(rpw, 27, HD, HD * 2, 32, 16, 2, 1);
+    mot = get_tensor_map_nd(out, 3, odims, ostrides, qa_tail, 2, 1);
+    if (!mqat || !mqbt || !mkvt || !mht || !mwt || !mot) return SAMQ_ERR_LAUNCH;
+  }
+  auto kern = attn_win3_kernel<HD>;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_win3 smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
+      return SAMQ_ERR_LAUNCH;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  const int n_items = B * heads;
+  dim3 grid(n_items < num_sms ? n_items : num_sms);
+  kern<<<grid, kWin3Threads, C::kSmemBytes, st>>>(*mqa, *mqat, *mqb, *mqbt, *mkv, *mkvt, *mh, *mht, *mw, *mwt, *mo, *mot,
+                                                 heads, n_items, scale, relw_mode);
+  count_launch();
+  return check_launch("attn_win3_kernel");
+}
+
+// ===========================================================================================
 // Global (64x64) attention, second design: two softmax warpgroups, software-pipelined.
 //
 // What the first design (attn_relpos_kernel<HD, false>) lost, measured with the clock64()
@@ -784,23 +1318,6 @@ int launch_attn_win(const void* qkv, const void* rph, const void* rpw, void* out
 // The two threads of a query row exchange partial maxima through shared memory once per tile
 // (one 256-thread named barrier); partial row sums are combined at the end.
 // ===========================================================================================
-#ifdef SAMQ_ATTN_PROFILE
-// developer-only wait-time breakdown (tests/micro/attn_prof.cu); never compiled into libsamq.so
-__device__ long long g_attn_prof[12][8];
-#define PROF_DECL long long pt0 = 0, pstart = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define PROF_BEGIN pt0 = clock64()
-#define PROF_END(i) pacc[i] += clock64() - pt0
-#define PROF_STAMP(i) pacc[i] = clock64() - pstart
-#define PROF_FLUSH                                                        \
-  if (lane == 0 && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 0) \
-    for (int i_ = 0; i_ < 8; ++i_) g_attn_prof[warp][i_] = pacc[i_]
-#else
-#define PROF_DECL
-#define PROF_BEGIN
-#define PROF_END(i)
-#define PROF_STAMP(i)
-#define PROF_FLUSH
-#endif
 // tcgen05.ld 32x32b.x32 straight into a slice of a float array (the instruction is .b32-typed)
 __device__ __forceinline__ void tmem_ld_x32f(uint32_t taddr, float (&r)[64], int o) {
   asm volatile(
@@ -1364,8 +1881,13 @@ extern "C" int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, cons
   const bool glob = (H == 64 && W == 64), win = (H == 14 && W == 14);
   SAMQ_REQUIRE(glob || win, SAMQ_ERR_BAD_SHAPE,
                "samq_attn_relpos_fwd: (H,W)=(%d,%d) not supported ((64,64) or (14,14))", H, W);
-  const char* wv = getenv("SAMQ_ATTN_WIN");   // "v1": first windowed design (two key tiles), ablation only
+  const char* wv = getenv("SAMQ_ATTN_WIN");   // ablations: "v1" first design (two key tiles), "v2" one CTA per q-tile
   const bool win_v1 = wv && strcmp(wv, "v1") == 0;
+  const bool win_v2 = wv && strcmp(wv, "v2") == 0;
+  if (!glob && !win_v1 && !win_v2) {
+    return hd == 64 ? launch_attn_win3<64>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
+                    : launch_attn_win3<80>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+  }
   const char* gv = getenv("SAMQ_ATTN_GLOB");  // "v1": first global design (one softmax warpgroup)
   const bool glob_v1 = gv && strcmp(gv, "v1") == 0;
   if (glob && !glob_v1) {

@@ -7,7 +7,8 @@
 int main(int argc, char** argv) {
   const int hd = argc > 1 ? atoi(argv[1]) : 80;
   const int B = argc > 2 ? atoi(argv[2]) : 8;
-  const int heads = 16, E = 64, S = E * E, D = heads * hd;
+  const int E = argc > 3 ? atoi(argv[3]) : 64;
+  const int heads = 16, S = E * E, D = heads * hd;
   std::vector<__half> h(static_cast<size_t>(B) * S * 3 * D);
   unsigned x = 12345u;
   for (auto& v : h) { x = x * 1664525u + 1013904223u; v = __float2half(((x >> 8) & 0xffff) / 65536.f - 0.5f); }
@@ -30,6 +31,17 @@ int main(int argc, char** argv) {
 #ifdef SAMQ_ATTN_PROFILE
   long long prof[12][8];
   cudaMemcpyFromSymbol(prof, samq::g_attn_prof, sizeof(prof));
+  if (E == 14) {
+    printf("windowed v3, one CTA, totals over its items (clk): wait t_full | bias gather | wait s_full | max pass | exp pass | wait o_full | drain | store\n");
+    for (int w = 0; w < 8; ++w)
+      printf("tile %c warp %d: %7lld %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", w < 4 ? 'A' : 'B', w & 3, prof[w][0], prof[w][1],
+             prof[w][2], prof[w][3], prof[w][4], prof[w][5], prof[w][6], prof[w][7]);
+    printf("MMA warps (clk totals): wait q_full | wait o_free | T issue->done | wait k_full+t_done | QK issue->done | wait v_full+p_full | PV issue->done\n");
+    for (int w = 9; w < 11; ++w)
+      printf("MMA tile %c: %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", w == 9 ? 'A' : 'B', prof[w][0], prof[w][1], prof[w][2],
+             prof[w][3], prof[w][4], prof[w][5], prof[w][6]);
+    return 0;
+  }
   const char* names[10] = {"sm g0 e0", "sm g0 e1", "sm g0 e2", "sm g0 e3", "sm g1 e0", "sm g1 e1", "sm g1 e2", "sm g1 e3", "TMA", "MMA"};
   printf("per-CTA totals over 32 key tiles (clk): softmax = wait s_full | max-exchange barrier | ex2+next-tile phase; "
          "TMA = wait k_empty | v_empty; MMA = wait k_full | p_full | v_full\n");
