@@ -70,6 +70,9 @@ __device__ __forceinline__ int map_row(int m, int M, const RowMap& rm) {
 
 // Lanes own features (TMEM lanes), registers own tokens; the block is transposed through a
 // 2 KB shared-memory tile so that global accesses are 16-byte row segments.
+// (ncu source view of the first version: the residual "prefetch" was a predicated load followed
+// by a predicated move, i.e. it waited for DRAM on the spot -- 21% of the proj GEMM's samples;
+// the tile was addressed through generic pointers.  Hence the explicit predicated / shared PTX.)
 template <bool GELU>
 struct EpiBlock {
   int dest[4];     // destination rows of the 4 row segments this lane stores (-1: skip)
@@ -84,33 +87,51 @@ struct EpiBlock {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       dest[it] = __shfl_sync(0xffffffffu, d, it * 8 + (lane >> 2));
-      rv[it] = (residual && dest[it] >= 0)
-                   ? *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(dest[it]) * N + (col0 + q * 8))
-                   : make_uint4(0, 0, 0, 0);
+      rv[it] = make_uint4(0, 0, 0, 0);
+      const int row = dest[it] >= 0 ? dest[it] : 0;
+      const __half* src = residual + static_cast<size_t>(row) * N + (col0 + q * 8);
+      const int on = (residual != nullptr) & (dest[it] >= 0);
+      // predicated load INTO the zero-initialised registers: nothing consumes them until finish()
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %5, 0;\n\t"
+          "@p ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t"
+          "}\n"
+          : "+r"(rv[it].x), "+r"(rv[it].y), "+r"(rv[it].z), "+r"(rv[it].w)
+          : "l"(src), "r"(on));
     }
   }
 
   __device__ __forceinline__ void finish(const uint32_t (&r)[32], float bv, __half* stage, int N,
                                          int col0, int lane, bool has_residual, __half* y) {
+    const uint32_t st = smem_u32(stage);
+    const uint32_t wr = st + lane * 2;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float v = __uint_as_float(r[j]) + bv;
       if (GELU) v = gelu_erf(v);
-      stage[j * 32 + lane] = __float2half_rn(v);
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + j * 64), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
     }
     __syncwarp();
     const int q = lane & 3;
+    const uint32_t rd = st + ((lane >> 2) * 32 + q * 8) * 2;
+    uint4 val[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(val[it].x), "=r"(val[it].y), "=r"(val[it].z), "=r"(val[it].w)
+                   : "r"(rd + it * 512));
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       if (dest[it] >= 0) {
-        uint4 val = *reinterpret_cast<const uint4*>(stage + (it * 8 + (lane >> 2)) * 32 + q * 8);
         if (has_residual) {   // fp16 add of two fp16 values, as the reference's `shortcut + x`
-          val.x = h2_add(val.x, rv[it].x);
-          val.y = h2_add(val.y, rv[it].y);
-          val.z = h2_add(val.z, rv[it].z);
-          val.w = h2_add(val.w, rv[it].w);
+          val[it].x = h2_add(val[it].x, rv[it].x);
+          val[it].y = h2_add(val[it].y, rv[it].y);
+          val[it].z = h2_add(val[it].z, rv[it].z);
+          val[it].w = h2_add(val[it].w, rv[it].w);
         }
-        *reinterpret_cast<uint4*>(y + static_cast<size_t>(dest[it]) * N + (col0 + q * 8)) = val;
+        *reinterpret_cast<uint4*>(y + static_cast<size_t>(dest[it]) * N + (col0 + q * 8)) = val[it];
       }
     }
     __syncwarp();

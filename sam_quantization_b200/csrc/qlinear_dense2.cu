@@ -89,7 +89,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int n0 = n_tile * 2 * kDBN + static_cast<int>(rank) * kDBN;
         const int m0 = m_tile * kDBM + static_cast<int>(rank) * (kDBM / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_relaxed(&empty[s], ph ^ 1);
           if (leader) mbar_arrive_expect_tx(&full[s], 2 * kDStageBytes);
           else mbar_arrive_cluster(lead_full + s * 8);
           uint8_t* stage = smem + s * kDStageBytes;

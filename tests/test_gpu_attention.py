@@ -37,6 +37,34 @@ def test_attention_test_op_shapes(cuda_device, B, E, heads, hd, relw):
     assert err <= ATOL and cos >= 0.9999, (err, mag, cos)
 
 
+@pytest.mark.parametrize("B,heads,hd", [(1, 1, 80), (1, 3, 64), (10, 16, 80), (37, 5, 64), (60, 16, 80)])
+def test_windowed_item_scheduling(cuda_device, B, heads, hd):
+    """The windowed kernel is persistent (one CTA per SM looping over (window, head) items):
+    fewer items than SMs, a ragged last round (160 = 148 + 12, 185 items) and many rounds."""
+    qkv, rph, rpw = make_inputs(B, 14, heads, hd, seed=7)
+    args = (qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), B, 14, 14, heads, hd ** -0.5)
+    out = ops.attn_relpos(*args)
+    ref = oe.attention_core(qkv, rph, rpw, B, 14, 14, heads, hd ** -0.5, "reference", round_tables=True)
+    err, mag, cos = report(out, ref)
+    assert not torch.isnan(out).any()
+    assert err <= ATOL and cos >= 0.9999, (err, mag, cos)
+    assert torch.equal(out, ops.attn_relpos(*args)), "run-to-run determinism"
+
+
+@pytest.mark.parametrize("env,val,B,E", [("SAMQ_ATTN_WIN", "v2", 25, 14), ("SAMQ_ATTN_WIN", "v1", 25, 14),
+                                         ("SAMQ_ATTN_GLOB", "v1", 1, 64)])
+def test_ablation_kernels_agree_with_default(cuda_device, monkeypatch, env, val, B, E):
+    """The earlier kernel designs stay selectable (SAMQ_ATTN_WIN=v1|v2, SAMQ_ATTN_GLOB=v1) for
+    A/B timing; they must compute the same function."""
+    qkv, rph, rpw = make_inputs(B, E, 4, 80, seed=11)
+    args = (qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), B, E, E, 4, 80 ** -0.5)
+    new = ops.attn_relpos(*args)
+    monkeypatch.setenv(env, val)
+    old = ops.attn_relpos(*args)
+    monkeypatch.delenv(env)
+    assert (new.float() - old.float()).abs().max().item() <= 1e-3
+
+
 def test_relw_modes_differ(cuda_device):
     qkv, rph, rpw = make_inputs(2, 14, 2, 64)
     a = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), 2, 14, 14, 2, 0.125, 0)
