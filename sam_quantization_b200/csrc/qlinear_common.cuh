@@ -73,7 +73,11 @@ __device__ __forceinline__ int map_row(int m, int M, const RowMap& rm) {
 // (ncu source view of the first version: the residual "prefetch" was a predicated load followed
 // by a predicated move, i.e. it waited for DRAM on the spot -- 21% of the proj GEMM's samples;
 // the tile was addressed through generic pointers.  Hence the explicit predicated / shared PTX.)
-template <bool GELU>
+// RES: 0 = the kernel has no residual, 1 = it always has one (unconditional loads: rows that are
+// not stored read row 0 and are ignored), 2 = decided at run time (predicated loads).  ptxas turns
+// a predicated load into "load to a temporary + predicated move", and the move waits for DRAM on
+// the spot, so the kernels that live on the residual path are compiled with RES = 1.
+template <bool GELU, int RES = 2>
 struct EpiBlock {
   int dest[4];     // destination rows of the 4 row segments this lane stores (-1: skip)
   uint4 rv[4];     // residual values for them
@@ -87,19 +91,25 @@ struct EpiBlock {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       dest[it] = __shfl_sync(0xffffffffu, d, it * 8 + (lane >> 2));
-      rv[it] = make_uint4(0, 0, 0, 0);
+      if (RES == 0) continue;
       const int row = dest[it] >= 0 ? dest[it] : 0;
       const __half* src = residual + static_cast<size_t>(row) * N + (col0 + q * 8);
-      const int on = (residual != nullptr) & (dest[it] >= 0);
-      // predicated load INTO the zero-initialised registers: nothing consumes them until finish()
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "setp.ne.b32 p, %5, 0;\n\t"
-          "@p ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t"
-          "}\n"
-          : "+r"(rv[it].x), "+r"(rv[it].y), "+r"(rv[it].z), "+r"(rv[it].w)
-          : "l"(src), "r"(on));
+      if (RES == 1) {
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rv[it].x), "=r"(rv[it].y), "=r"(rv[it].z), "=r"(rv[it].w)
+                     : "l"(src));
+      } else {
+        rv[it] = make_uint4(0, 0, 0, 0);
+        const int on = (residual != nullptr) & (dest[it] >= 0);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "@p ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t"
+            "}\n"
+            : "+r"(rv[it].x), "+r"(rv[it].y), "+r"(rv[it].z), "+r"(rv[it].w)
+            : "l"(src), "r"(on));
+      }
     }
   }
 
@@ -107,11 +117,46 @@ struct EpiBlock {
                                          int col0, int lane, bool has_residual, __half* y) {
     const uint32_t st = smem_u32(stage);
     const uint32_t wr = st + lane * 2;
+    if (!GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float v = __uint_as_float(r[j]) + bv;
-      if (GELU) v = gelu_erf(v);
-      asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + j * 64), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
+      for (int j = 0; j < 32; ++j) {
+        const float v = __uint_as_float(r[j]) + bv;
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + j * 64), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
+      }
+    } else {
+      // gelu_erf() over the 32 tokens, software-pipelined by hand in three stages so that the
+      // two MUFU ops of an element (rcp, ex2: one warp-instruction per 8 clk each) are spread
+      // between the ~12 FMA-pipe instructions of its neighbours instead of being issued as two
+      // bursts of 32 (volatile asm keeps the order)
+      float ax[32], tt[32], pe[32];
+#pragma unroll
+      for (int j = 0; j < 34; ++j) {
+        if (j < 32) {
+          ax[j] = __uint_as_float(r[j]) + bv;           // v (sign kept), |v| via fabsf below
+          const float d = fmaf(fabsf(ax[j]), 0.3275911f * 0.70710678118654752440f, 1.0f);
+          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(tt[j]) : "f"(d));
+        }
+        if (j >= 1 && j < 33) {
+          const int i = j - 1;
+          const float t = tt[i], a = fabsf(ax[i]);
+          float poly = 0.5f * 1.061405429f;
+          poly = fmaf(poly, t, 0.5f * -1.453152027f);
+          poly = fmaf(poly, t, 0.5f * 1.421413741f);
+          poly = fmaf(poly, t, 0.5f * -0.284496736f);
+          poly = fmaf(poly, t, 0.5f * 0.254829592f);
+          poly *= t;
+          const float u = a * 0.84932180028801904272f;  // |x| * sqrt(log2(e) / 2)
+          float e;
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
+          pe[i] = poly * e;
+        }
+        if (j >= 2) {
+          const int i = j - 2;
+          const float v = ax[i];
+          const float g = fmaf(-pe[i], fabsf(v), fmaxf(v, 0.f));
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + i * 64), "h"(__half_as_ushort(__float2half_rn(g))) : "memory");
+        }
+      }
     }
     __syncwarp();
     const int q = lane & 3;
@@ -125,7 +170,7 @@ struct EpiBlock {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       if (dest[it] >= 0) {
-        if (has_residual) {   // fp16 add of two fp16 values, as the reference's `shortcut + x`
+        if (RES == 1 || (RES == 2 && has_residual)) {   // fp16 add of two fp16 values, as the reference's `shortcut + x`
           val[it].x = h2_add(val[it].x, rv[it].x);
           val[it].y = h2_add(val[it].y, rv[it].y);
           val[it].z = h2_add(val[it].z, rv[it].z);

@@ -28,11 +28,30 @@ constexpr int kDEpiBytes = 8 * 2048;
 constexpr int kDSmemData = kDStages * kDStageBytes;
 constexpr int kDSmemBytes = kDSmemData + kDEpiBytes + (2 * kDStages + 4) * 8 + 16 + 1024;
 
-template <bool GELU>
+#ifdef SAMQ_GEMM_PROFILE
+// developer-only clock64 breakdown (tests/micro/gemm_prof.cu); never compiled into libsamq.so
+__device__ long long g_gemm_prof[2][10][8];
+#define GP_DECL long long gt0 = 0, gacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define GP_BEGIN gt0 = clock64()
+#define GP_END(i) gacc[i] += clock64() - gt0
+#define GP_MAX(i) { long long d_ = clock64() - gt0; gacc[i] = d_ > gacc[i] ? d_ : gacc[i]; }
+#define GP_FLUSH                                                                     \
+  if (lane == 0 && (blockIdx.x >> 1) == 5)                                           \
+    for (int i_ = 0; i_ < 8; ++i_) g_gemm_prof[blockIdx.x & 1][warp][i_] = gacc[i_]
+#else
+#define GP_DECL
+#define GP_BEGIN
+#define GP_END(i)
+#define GP_MAX(i)
+#define GP_FLUSH
+#endif
+
+template <bool GELU, bool RES>
 __global__ void __launch_bounds__(kDThreads, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N, int K,
               const RowMap rowmap) {
+  GP_DECL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -108,8 +127,12 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       bool rdy = total_kb > 0 && mbar_test(&full[0], 0);
       for (int kbc = 0; kbc < total_kb; ++kbc) {
         const int ab = lt & 1;
+        GP_BEGIN;
         if (kb == 0) mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);
+        GP_END(0);
+        GP_BEGIN;
         if (!rdy) mbar_wait(&full[s], ph);
+        GP_END(1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * kDBM;
         const uint64_t a_desc = make_smem_desc(smem_u32(smem + s * kDStageBytes), 0, 1024, kLayoutSw128);
@@ -138,23 +161,37 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const int grp = warp < 4 ? 0 : 1;
     int lt = 0;
     __half* stage = reinterpret_cast<__half*>(sepi + (grp * 4 + e) * 2048);
+    constexpr int kChunks = kDBM / 64;           // 32-token chunks per group and tile
+    const int c0 = grp * kChunks;
+    auto feature_base = [&](int t) { return (t % NT) * 2 * kDBN + static_cast<int>(rank) * kDBN + e * 32; };
+    // The residual rows of a chunk are requested one chunk ahead (across tile boundaries too):
+    // with the request issued right before the chunk's own TMEM load, the ~1.5k clk of DRAM
+    // latency was exposed in every chunk and the proj GEMM was epilogue-bound (12.0k clk of
+    // epilogue per tile against a 10.2k clk main loop; 5.9k without the residual).
+    EpiBlock<GELU, RES ? 1 : 0> blk_a, blk_b;
+    if (pair < num_tiles) blk_a.prefetch((pair / NT) * kDBM + c0 * 32, M, N, feature_base(pair), lane, residual, rowmap);
     for (int t = pair; t < num_tiles; t += npairs, ++lt) {
-      const int n_tile = t % NT, m_tile = t / NT;
-      const int nb = n_tile * 2 * kDBN + static_cast<int>(rank) * kDBN + e * 32;
+      const int m_tile = t / NT;
+      const int nb = feature_base(t);
       const int ab = lt & 1;
       const float bv = bias ? __half2float(bias[nb + lane]) : 0.f;
+      const int t_next = t + npairs;
+      GP_BEGIN;
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      GP_END(0);
+      GP_BEGIN;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * kDBM + (static_cast<uint32_t>(e * 32) << 16);
-#pragma unroll 1
-      for (int c = grp * (kDBM / 64); c < (grp + 1) * (kDBM / 64); ++c) {
-        const int m0 = m_tile * kDBM + c * 32;
-        EpiBlock<GELU> blk;
-        blk.prefetch(m0, M, N, nb, lane, residual, rowmap);
+      // one chunk: request the residual of the chunk after it, drain this one
+      auto chunk = [&](int c, EpiBlock<GELU, RES ? 1 : 0>& cur, EpiBlock<GELU, RES ? 1 : 0>& nxt, bool last) {
+        // (one call site: two would merge through register moves that wait for the loads)
+        const int m_next = last ? (t_next / NT) * kDBM + c0 * 32 : m_tile * kDBM + (c + 1) * 32;
+        const int nb_next = last ? feature_base(t_next) : nb;
+        nxt.prefetch(m_next, (last && t_next >= num_tiles) ? 0 : M, N, nb_next, lane, residual, rowmap);
         uint32_t r[32];
         tmem_ld_x32(d_tmem + c * 32, r);
         tmem_ld_wait();
-        if (c == (grp + 1) * (kDBM / 64) - 1) {
+        if (last) {
           // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -162,11 +199,21 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             if (leader) mbar_arrive(&acc_empty[ab]);
             else mbar_arrive_cluster(lead_acc_empty + ab * 8);
           }
+          GP_END(1);
+          GP_MAX(3);
         }
-        blk.finish(r, bv, stage, N, nb, lane, residual != nullptr, y);
+        cur.finish(r, bv, stage, N, nb, lane, residual != nullptr, y);
+      };
+#pragma unroll 1
+      for (int cc = 0; cc < kChunks; cc += 2) {
+        chunk(c0 + cc, blk_a, blk_b, false);
+        chunk(c0 + cc + 1, blk_b, blk_a, cc + 2 == kChunks);
       }
+      GP_END(2);
+      GP_MAX(4);
     }
   }
+  GP_FLUSH;
 
   tc_fence_before();
   cluster_sync_all();
@@ -185,15 +232,18 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
   const CUtensorMap* mw = get_tensor_map_2d(wt, N, K, static_cast<uint64_t>(K) * 2, kDBN, kDBK, 2, 3);
   if (!mx || !mw) return SAMQ_ERR_LAUNCH;
   const bool gelu = epilogue == SAMQ_EPI_GELU;
-  auto kern = gelu ? dense2_kernel<true> : dense2_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[gelu]) {
+  const bool res = residual != nullptr;
+  auto kern = gelu ? (res ? dense2_kernel<true, true> : dense2_kernel<true, false>)
+                   : (res ? dense2_kernel<false, true> : dense2_kernel<false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  const int variant = (gelu ? 2 : 0) + (res ? 1 : 0);
+  if (!attr_set[variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmemBytes);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(dense2 smem=%d): %s", kDSmemBytes, cudaGetErrorString(e));
       return SAMQ_ERR_LAUNCH;
     }
-    attr_set[gelu] = true;
+    attr_set[variant] = true;
   }
   const int NT = N / (2 * kDBN);
   const int64_t MT = (M + kDBM - 1) / kDBM;
