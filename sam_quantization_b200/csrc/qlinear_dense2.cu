@@ -15,8 +15,18 @@
 namespace samq {
 namespace {
 
-constexpr int kDThreads = 320;            // warps 0-3 + 6-9 epilogue (two groups), warp 4 TMA, warp 5 MMA + TMEM alloc
-constexpr int kDWarpTma = 4, kDWarpMma = 5;
+// Warps 0 .. kEpiWarps-1 drain the accumulator (groups of four = TMEM lane quadrants; group g owns
+// token columns [256 g / G, 256 (g+1) / G)), then one TMA warp and one MMA + TMEM-alloc warp.
+// (16 epilogue warps for the GELU kernel were tried: each warp's share halves but the kernel
+// time does not move -- 316 us for 32768 x 1280 x 5120 either way, 283 us without GELU -- so
+// the GELU cost is not an issue-slot or latency problem of the epilogue warps; 8 it stays.)
+template <bool GELU>
+struct DCfg {
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kWarpTma = kEpiWarps, kWarpMma = kEpiWarps + 1;
+  static constexpr int kThreads = (kEpiWarps + 2) * 32;
+  static constexpr int kEpiBytes = kEpiWarps * 2048;
+};
 constexpr int kDBM = 256;                 // tokens per pair tile (UMMA N)
 constexpr int kDBN = 128;                 // features per CTA   (UMMA M = 256 over the pair)
 constexpr int kDBK = 64;
@@ -24,13 +34,14 @@ constexpr int kDStages = 6;
 constexpr int kDABytes = kDBN * kDBK * 2;          // 16 KB
 constexpr int kDXBytes = (kDBM / 2) * kDBK * 2;    // 16 KB (this CTA's half of the x tile)
 constexpr int kDStageBytes = kDABytes + kDXBytes;
-constexpr int kDEpiBytes = 8 * 2048;
 constexpr int kDSmemData = kDStages * kDStageBytes;
-constexpr int kDSmemBytes = kDSmemData + kDEpiBytes + (2 * kDStages + 4) * 8 + 16 + 1024;
+template <bool GELU>
+constexpr int kDSmemBytes = kDSmemData + DCfg<GELU>::kEpiBytes + (2 * kDStages + 4) * 8 + 16 + 1024;
+static_assert(kDSmemBytes<true> <= 232448, "shared memory budget");
 
 #ifdef SAMQ_GEMM_PROFILE
 // developer-only clock64 breakdown (tests/micro/gemm_prof.cu); never compiled into libsamq.so
-__device__ long long g_gemm_prof[2][10][8];
+__device__ long long g_gemm_prof[2][18][8];
 #define GP_DECL long long gt0 = 0, gacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define GP_BEGIN gt0 = clock64()
 #define GP_END(i) gacc[i] += clock64() - gt0
@@ -47,7 +58,7 @@ __device__ long long g_gemm_prof[2][10][8];
 #endif
 
 template <bool GELU, bool RES>
-__global__ void __launch_bounds__(kDThreads, 1)
+__global__ void __launch_bounds__(DCfg<GELU>::kThreads, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N, int K,
               const RowMap rowmap) {
@@ -56,7 +67,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sepi = smem + kDSmemData;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDSmemData + kDEpiBytes);
+  using DC = DCfg<GELU>;
+  constexpr int kDWarpTma = DC::kWarpTma, kDWarpMma = DC::kWarpMma;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDSmemData + DC::kEpiBytes);
   uint64_t* full = bars;                       // leader's is the live one
   uint64_t* empty = full + kDStages;           // multicast commit -> both CTAs
   uint64_t* acc_full = empty + kDStages;       // multicast commit -> both CTAs
@@ -81,7 +94,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 16);   // 8 epilogue warps of each CTA
+      mbar_init(&acc_empty[i], 2 * DC::kEpiWarps);   // the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -158,10 +171,10 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     // two groups of four warps (TMEM lane quadrant = warp % 4); group 0 drains token columns
     // [0, 128), group 1 drains [128, 256) of the accumulator
     const int e = warp & 3;
-    const int grp = warp < 4 ? 0 : 1;
+    const int grp = warp >> 2;
     int lt = 0;
-    __half* stage = reinterpret_cast<__half*>(sepi + (grp * 4 + e) * 2048);
-    constexpr int kChunks = kDBM / 64;           // 32-token chunks per group and tile
+    __half* stage = reinterpret_cast<__half*>(sepi + warp * 2048);
+    constexpr int kChunks = kDBM / 32 / (DC::kEpiWarps / 4);   // 32-token chunks per group and tile
     const int c0 = grp * kChunks;
     auto feature_base = [&](int t) { return (t % NT) * 2 * kDBN + static_cast<int>(rank) * kDBN + e * 32; };
     // The residual rows of a chunk are requested one chunk ahead (across tile boundaries too):
@@ -237,10 +250,11 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
                    : (res ? dense2_kernel<false, true> : dense2_kernel<false, false>);
   static bool attr_set[4] = {false, false, false, false};
   const int variant = (gelu ? 2 : 0) + (res ? 1 : 0);
+  const int smem_bytes = gelu ? kDSmemBytes<true> : kDSmemBytes<false>;
   if (!attr_set[variant]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(dense2 smem=%d): %s", kDSmemBytes, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(dense2 smem=%d): %s", smem_bytes, cudaGetErrorString(e));
       return SAMQ_ERR_LAUNCH;
     }
     attr_set[variant] = true;
@@ -252,8 +266,8 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
   const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kDThreads);
-  cfg.dynamicSmemBytes = kDSmemBytes;
+  cfg.blockDim = dim3(gelu ? DCfg<true>::kThreads : DCfg<false>::kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -30,11 +30,11 @@ int main(int argc, char** argv) {
     printf("rc %d  %.1f us  %.1f TFLOP/s (%s)\n", rc, ms * 1e3, 2.0 * M * K * N / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
   }
 #ifdef SAMQ_GEMM_PROFILE
-  long long prof[2][10][8];
+  long long prof[2][18][8];
   cudaMemcpyFromSymbol(prof, samq::g_gemm_prof, sizeof(prof));
-  printf("pair 5, per warp totals (clk): epilogue: wait acc_full | acc_full->release | total busy | max release | max tile ;  MMA (warp 5): wait acc_empty | wait full\n");
+  printf("pair 5, per warp totals (clk): epilogue: wait acc_full | acc_full->release | total busy | max release | max tile ;  MMA (last warp): wait acc_empty | wait full\n");
   for (int r = 0; r < 2; ++r)
-    for (int wp = 0; wp < 10; ++wp)
+    for (int wp = 0; wp < (epi ? 18 : 10); ++wp)
       printf("cta %d warp %d: %9lld %9lld %9lld %9lld %9lld\n", r, wp, prof[r][wp][0], prof[r][wp][1], prof[r][wp][2], prof[r][wp][3], prof[r][wp][4]);
 #endif
   return 0;
