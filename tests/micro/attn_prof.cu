@@ -32,9 +32,9 @@ int main(int argc, char** argv) {
   long long prof[12][8];
   cudaMemcpyFromSymbol(prof, samq::g_attn_prof, sizeof(prof));
   if (E == 14) {
-    printf("windowed v3, one CTA, totals over its items (clk): wait t_full | bias gather | wait s_full | max pass | exp pass | wait o_full | drain | store\n");
+    printf("windowed v4, one CTA, totals over its units (clk): wait s_full | max pass | exchange barrier | (wait t_full) | (wait o_full) | drain total | gather total | exp pass\n");
     for (int w = 0; w < 8; ++w)
-      printf("tile %c warp %d: %7lld %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", w < 4 ? 'A' : 'B', w & 3, prof[w][0], prof[w][1],
+      printf("wg %c warp %d: %7lld %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", w < 4 ? 'A' : 'B', w & 3, prof[w][0], prof[w][1],
              prof[w][2], prof[w][3], prof[w][4], prof[w][5], prof[w][6], prof[w][7]);
     printf("MMA warps (clk totals): wait q_full | wait o_free | T issue->done | wait k_full+t_done | QK issue->done | wait v_full+p_full | PV issue->done\n");
     for (int w = 9; w < 11; ++w)
