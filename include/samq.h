@@ -117,6 +117,18 @@ int samq_qlinear_unpartition_fwd(const void* x, const int32_t* qweight, const in
                                  int W, int ws, int K, int N, int bits, int groupsize,
                                  void* stream);
 
+/* qkv GEMM fused with window_partition (QuantAttention.forward's qkv_proj,
+ * fused_attention.py:110, applied to the output of image_encoder.py:196-198, 282-306):
+ * x holds the normalised tokens in IMAGE order, fp16 [B, H, W, K]; the result row of image token
+ * (b, h, w) is written to window token (b, h/ws, w/ws, h%ws, w%ws) of y fp16
+ * [B*nH*nW, ws, ws, N].  The rows of the zero-padding tokens, for which the reference multiplies
+ * zero rows, are set to `bias` (0 without a bias) -- the value fp16(0 + bias) that GEMM produces --
+ * without being multiplied.  Other arguments as samq_qlinear_fwd. */
+int samq_qlinear_partition_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                               const void* scales, const int32_t* g_idx, const void* bias, void* y,
+                               void* workspace, int B, int H, int W, int ws, int K, int N, int bits,
+                               int groupsize, void* stream);
+
 /* Dense fp16 GEMM on the same tcgen05 kernel: y = epi(x . Wt^T + bias) + residual
  * with Wt fp16 [N, K] (already dequantised).  Used for the ablation "dequantise
  * once, then GEMM" and by samq_qlinear_fwd for the non-int4 formats. */
@@ -137,6 +149,18 @@ int samq_dense_linear_fwd(const void* x, const void* wt, const void* bias,
 int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
                          void* out, int B, int H, int W, int heads, int hd,
                          float scale, int relw_mode, void* stream);
+
+/* Windowed attention with window_unpartition + crop fused into the store
+ * (QuantAttention.forward on the partitioned tokens, fused_attention.py:107-149, followed by
+ * image_encoder.py:201-203, 309-333): qkv is the packed qkv GEMM output of the WINDOWED tokens,
+ * fp16 [B*nH*nW, ws, ws, 3*heads*hd] (nH = ceil(H/ws), the zero-padding tokens included as keys
+ * exactly like the reference); out is fp16 [B, H, W, heads*hd] in IMAGE order -- token (i, j) of
+ * window (b, wh, ww) is written to (b, wh*ws+i, ww*ws+j), tokens outside the image are dropped
+ * (each window tile leaves as one TMA box; out-of-bounds elements of a box are not written).
+ * ws must be 14; other arguments as samq_attn_relpos_fwd. */
+int samq_attn_relpos_unpartition_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
+                                     void* out, int B, int H, int W, int ws, int heads, int hd,
+                                     float scale, int relw_mode, void* stream);
 
 /* LayerNorm / window partition ------------------------------------------------
  * y = LayerNorm(x; gamma, beta, eps) over the last dim, fp32 statistics

@@ -49,6 +49,11 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     ),
+    "samq_qlinear_partition_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    ),
     "samq_dense_linear_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
@@ -56,6 +61,11 @@ SIGNATURES = {
     "samq_attn_relpos_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    ),
+    "samq_attn_relpos_unpartition_fwd": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+         c_void_p],
     ),
     "samq_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "samq_layernorm_partition_fwd": (

@@ -821,11 +821,20 @@ template <int HD>
 struct W3Cfg {
   static constexpr int E = 14, S = 196, SP = 208;
   static constexpr int kTail = HD - 64;
-  static constexpr int kRowsB = 80;                                   // tile B: tokens 128..195 (+ zero rows)
+  // The window's 196 tokens = 14 rows of 14.  Tile A stores rows 0-8 (tokens 0..125; its MMA rows
+  // 126, 127 are computed and ignored), tile B rows 9-13 (tokens 126..195): both are rectangles of
+  // the window, so each tile's O is ONE TMA store box {hd, 14, rows} -- into the windowed layout or
+  // straight into image order (window_unpartition + crop for free: out-of-image elements of a box
+  // are not written).
+  static constexpr int kTokB = 126, kRowsA = 126, kValidB = S - kTokB;  // 70
+  static constexpr int kRowsB = 72;                                   // Q rows loaded for tile B (>= 70, atoms of 8)
   static constexpr int kQAMain = 128 * 128, kQBMain = kRowsB * 128;
   static constexpr int kQATail = kTail ? 128 * 32 : 0, kQBTail = kTail ? kRowsB * 32 : 0;
-  static constexpr int oQA = 0, oQB = oQA + kQAMain, oQAT = oQB + kQBMain, oQBT = oQAT + kQATail;
+  // [QA main | QA tail | QB main | QB tail]: a tile's main + tail are adjacent because its O is
+  // staged over both as plain rows of hd fp16 (A: 126 x 2 hd <= 20480 / 16384 B, B: 70 x 2 hd)
+  static constexpr int oQA = 0, oQAT = oQA + kQAMain, oQB = oQAT + kQATail, oQBT = oQB + kQBMain;
   static constexpr int kQStage = ((oQBT + kQBTail + 1023) / 1024) * 1024;
+  static_assert(kRowsA * HD * 2 <= kQAMain + kQATail && kValidB * HD * 2 <= kQBMain + kQBTail, "O staging fits");
   static constexpr int kKVMain = SP * 128, kKVTail = kTail ? SP * 32 : 0;
   static constexpr int oKM = 0, oVM = kKVMain, oKT = 2 * kKVMain, oVT = oKT + kKVTail;
   static constexpr int kKVStage = ((oVT + kKVTail + 1023) / 1024) * 1024;
@@ -850,8 +859,8 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
                  const __grid_constant__ CUtensorMap map_kv_main, const __grid_constant__ CUtensorMap map_kv_tail,
                  const __grid_constant__ CUtensorMap map_rph_main, const __grid_constant__ CUtensorMap map_rph_tail,
                  const __grid_constant__ CUtensorMap map_rpw_main, const __grid_constant__ CUtensorMap map_rpw_tail,
-                 const __grid_constant__ CUtensorMap map_o_main, const __grid_constant__ CUtensorMap map_o_tail,
-                 int heads, int n_items, float scale, int relw_mode) {
+                 const __grid_constant__ CUtensorMap map_o_a, const __grid_constant__ CUtensorMap map_o_b,
+                 int heads, int n_items, float scale, int relw_mode, int img_nh, int img_nw) {
   using C = W3Cfg<HD>;
   constexpr int E = C::E, S = C::S, SP = C::SP;
   PROF_DECL;
@@ -916,10 +925,10 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
         mbar_wait(&q_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&q_full[st], C::kQAMain + C::kQBMain + C::kQATail + C::kQBTail);
         tma_load_3d(sQ + C::oQA, &map_qa_main, &q_full[st], head * HD, 0, b);
-        tma_load_3d(sQ + C::oQB, &map_qb_main, &q_full[st], head * HD, 128, b);
+        tma_load_3d(sQ + C::oQB, &map_qb_main, &q_full[st], head * HD, C::kTokB, b);
         if (C::kTail) {
           tma_load_3d(sQ + C::oQAT, &map_qa_tail, &q_full[st], head * HD + 64, 0, b);
-          tma_load_3d(sQ + C::oQBT, &map_qb_tail, &q_full[st], head * HD + 64, 128, b);
+          tma_load_3d(sQ + C::oQBT, &map_qb_tail, &q_full[st], head * HD + 64, C::kTokB, b);
         }
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], C::kKVMain + C::kKVTail);
@@ -1021,19 +1030,18 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
     const int row = e * 32 + lane;                    // row of the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(e * 32) << 16;
     const uint32_t region = tmem_base + X * SP + lane_off;
-    const int m = X * 128 + row;                      // token inside the window
-    const bool valid = m < S;
-    const bool warp_valid = (X * 128 + e * 32) < S;   // warp-uniform: any valid row in this warp
+    const int m = X * C::kTokB + row;                 // token inside the window
+    const int n_valid = X ? C::kValidB : C::kRowsA;   // rows of this tile that are stored
+    const bool valid = row < n_valid;
+    const bool warp_valid = e * 32 < n_valid;         // warp-uniform: any valid row in this warp
     const int mh = valid ? m / E : 0, mw = valid ? m % E : 0;
     // distinct table windows needed by this warp: image rows of its first / last valid token
-    const int m_first = X * 128 + e * 32, m_last = min(m_first + 31, S - 1);
+    const int m_first = X * C::kTokB + e * 32, m_last = X * C::kTokB + min(e * 32 + 31, n_valid - 1);
     const int vh_lo = m_first / E, vh_hi = m_last / E;
     float c_scale = scale * kLog2e;
     asm volatile("mov.b32 %0, %0;" : "+f"(c_scale));
-    // this row's O staging addresses inside the Q slot (same swizzles as the TMA tiles)
-    const uint32_t o_main_off = (X ? C::oQB : C::oQA) + (row >> 3) * 1024 + (row & 7) * 128;
-    const uint32_t o_tail_off = (X ? C::oQBT : C::oQAT) + (row >> 3) * 256 + (row & 7) * 32;
-    const bool stage_row = X == 0 || row < C::kRowsB;
+    // this row's O staging address inside the tile's Q slot: plain rows of hd fp16
+    const uint32_t o_row_off = (X ? C::oQB : C::oQA) + row * (HD * 2);
 
     int n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
@@ -1206,40 +1214,32 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
       {
         const float inv_l = warp_valid ? 1.f / l : 0.f;
         const uint32_t o_tmem = region + C::cO;
-        const uint32_t swz = row & 7;
-        uint8_t* o_main = sQ + o_main_off;
-        uint8_t* o_tail = sQ + o_tail_off;
+        uint4* o_row = reinterpret_cast<uint4*>(sQ + o_row_off);
+        auto pack8 = [&](const uint32_t* r) {
+          uint4 o;
+          o.x = pack_h2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+          o.y = pack_h2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+          o.z = pack_h2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+          o.w = pack_h2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+          return o;
+        };
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
           tmem_ld_x32(o_tmem + c * 32, r);
           tmem_ld_wait();
-          if (stage_row) {
+          if (valid) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 o;
-              o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
-              o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
-              o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
-              o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(o_main + (((c * 4 + v) ^ swz) << 4)) = o;
-            }
+            for (int v = 0; v < 4; ++v) o_row[c * 4 + v] = pack8(r + 8 * v);
           }
         }
         if (C::kTail) {
           uint32_t r[16];
           tmem_ld_x16(o_tmem + 64, r);
           tmem_ld_wait();
-          if (stage_row) {
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              uint4 o;
-              o.x = pack_h2(__uint_as_float(r[8 * v + 0]) * inv_l, __uint_as_float(r[8 * v + 1]) * inv_l);
-              o.y = pack_h2(__uint_as_float(r[8 * v + 2]) * inv_l, __uint_as_float(r[8 * v + 3]) * inv_l);
-              o.z = pack_h2(__uint_as_float(r[8 * v + 4]) * inv_l, __uint_as_float(r[8 * v + 5]) * inv_l);
-              o.w = pack_h2(__uint_as_float(r[8 * v + 6]) * inv_l, __uint_as_float(r[8 * v + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(o_tail + ((v ^ ((row >> 2) & 1)) << 4)) = o;
-            }
+          if (valid) {
+            o_row[8] = pack8(r);
+            o_row[9] = pack8(r + 8);
           }
         }
       }
@@ -1251,9 +1251,17 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
       fence_proxy_async_smem();                       // staging writes -> visible to the TMA engine
       named_bar_sync(1 + X, 128);
       if (e == 0 && lane == 0) {
-        // queued without waiting; the slot is released during the next item (see the max pass)
-        tma_store_3d(&map_o_main, sQ + (X ? C::oQB : C::oQA), head * HD, X * 128, b);
-        if (C::kTail) tma_store_3d(&map_o_tail, sQ + (X ? C::oQBT : C::oQAT), head * HD + 64, X * 128, b);
+        // queued without waiting; the slot is released during the next item (see the max pass).
+        // One box {hd, 14 columns, 9 | 5 rows} of the window: windowed layout (img_nw == 0) or the
+        // window's place in the [B, H, W, D] image (out-of-image rows / columns are clipped).
+        int c1 = 0, c2 = X ? 9 : 0, c3 = b;
+        if (img_nw > 0) {
+          const int ww = b % img_nw, t = b / img_nw;
+          c1 = ww * E;
+          c2 += (t % img_nh) * E;
+          c3 = t / img_nh;
+        }
+        tma_store_4d(X ? &map_o_b : &map_o_a, sQ + (X ? C::oQB : C::oQA), head * HD, c1, c2, c3);
         tma_store_commit();
       }
       PROF_END(7);
@@ -1272,14 +1280,12 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
 
 template <int HD>
 int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads, float scale,
-                     int relw_mode, cudaStream_t st) {
+                     int relw_mode, int img_h, int img_w, cudaStream_t st) {
   using C = W3Cfg<HD>;
   const int D = heads * HD;
   const uint64_t row_bytes = static_cast<uint64_t>(3) * D * 2;
   uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
   uint64_t strides[2] = {row_bytes, row_bytes * C::S};
-  uint64_t odims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(C::S), static_cast<uint64_t>(B)};
-  uint64_t ostrides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(D) * 2 * C::S};
   uint32_t qa_main[3] = {64, 128, 1}, qa_tail[3] = {16, 128, 1};
   uint32_t qb_main[3] = {64, C::kRowsB, 1}, qb_tail[3] = {16, C::kRowsB, 1};
   uint32_t kv_main[3] = {64, static_cast<uint32_t>(C::SP), 1}, kv_tail[3] = {16, static_cast<uint32_t>(C::SP), 1};
@@ -1288,19 +1294,26 @@ int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* ou
   const CUtensorMap* mkv = get_tensor_map_nd(qkv, 3, dims, strides, kv_main, 2, 3);
   const CUtensorMap* mh = get_tensor_map_2d(rph, 27, HD, HD * 2, 32, 64, 2, 3);
   const CUtensorMap* mw = get_tensor_map_2d(rpw, 27, HD, HD * 2, 32, 64, 2, 3);
-  // O tiles are stored with the 128-row box for both tiles: tile B's rows 68.. are tokens >= 196
-  // and are clipped by the tensor bounds
-  const CUtensorMap* mo = get_tensor_map_nd(out, 3, odims, ostrides, qa_main, 2, 3);
-  if (!mqa || !mqb || !mkv || !mh || !mw || !mo) return SAMQ_ERR_LAUNCH;
-  const CUtensorMap *mqat = mqa, *mqbt = mqb, *mkvt = mkv, *mht = mh, *mwt = mw, *mot = mo;
+  // O: 4-D view (d, column, row, window | image) of the windowed [B, 14, 14, D] or of the image-order
+  // [B / (nH nW), img_h, img_w, D] output; tile A stores window rows 0-8, tile B rows 9-13
+  const int img_nh = img_h > 0 ? (img_h + C::E - 1) / C::E : 0, img_nw = img_w > 0 ? (img_w + C::E - 1) / C::E : 0;
+  const uint64_t ow = img_w > 0 ? img_w : C::E, oh = img_h > 0 ? img_h : C::E;
+  const uint64_t ob = img_w > 0 ? static_cast<uint64_t>(B) / (img_nh * img_nw) : static_cast<uint64_t>(B);
+  uint64_t odims[4] = {static_cast<uint64_t>(D), ow, oh, ob};
+  uint64_t ostrides[3] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(D) * 2 * ow, static_cast<uint64_t>(D) * 2 * ow * oh};
+  uint32_t box_a[4] = {static_cast<uint32_t>(HD), static_cast<uint32_t>(C::E), 9, 1};
+  uint32_t box_b[4] = {static_cast<uint32_t>(HD), static_cast<uint32_t>(C::E), 5, 1};
+  const CUtensorMap* moa = get_tensor_map_nd(out, 4, odims, ostrides, box_a, 2, 0);
+  const CUtensorMap* mob = get_tensor_map_nd(out, 4, odims, ostrides, box_b, 2, 0);
+  if (!mqa || !mqb || !mkv || !mh || !mw || !moa || !mob) return SAMQ_ERR_LAUNCH;
+  const CUtensorMap *mqat = mqa, *mqbt = mqb, *mkvt = mkv, *mht = mh, *mwt = mw;
   if (C::kTail) {
     mqat = get_tensor_map_nd(qkv, 3, dims, strides, qa_tail, 2, 1);
     mqbt = get_tensor_map_nd(qkv, 3, dims, strides, qb_tail, 2, 1);
     mkvt = get_tensor_map_nd(qkv, 3, dims, strides, kv_tail, 2, 1);
     mht = get_tensor_map_2d(rph, 27, HD, HD * 2, 32, 16, 2, 1);
     mwt = get_tensor_map_2d(rpw, 27, HD, HD * 2, 32, 16, 2, 1);
-    mot = get_tensor_map_nd(out, 3, odims, ostrides, qa_tail, 2, 1);
-    if (!mqat || !mqbt || !mkvt || !mht || !mwt || !mot) return SAMQ_ERR_LAUNCH;
+    if (!mqat || !mqbt || !mkvt || !mht || !mwt) return SAMQ_ERR_LAUNCH;
   }
   auto kern = attn_win3_kernel<HD>;
   static bool attr_set = false;
@@ -1318,8 +1331,8 @@ int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* ou
   }
   const int n_items = B * heads;
   dim3 grid(n_items < num_sms ? n_items : num_sms);
-  kern<<<grid, kWin3Threads, C::kSmemBytes, st>>>(*mqa, *mqat, *mqb, *mqbt, *mkv, *mkvt, *mh, *mht, *mw, *mwt, *mo, *mot,
-                                                 heads, n_items, scale, relw_mode);
+  kern<<<grid, kWin3Threads, C::kSmemBytes, st>>>(*mqa, *mqat, *mqb, *mqbt, *mkv, *mkvt, *mh, *mht, *mw, *mwt, *moa, *mob,
+                                                 heads, n_items, scale, relw_mode, img_nh, img_nw);
   count_launch();
   return check_launch("attn_win3_kernel");
 }
@@ -1913,8 +1926,8 @@ extern "C" int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, cons
   const bool win_v1 = wv && strcmp(wv, "v1") == 0;
   const bool win_v2 = wv && strcmp(wv, "v2") == 0;
   if (!glob && !win_v1 && !win_v2) {
-    return hd == 64 ? launch_attn_win3<64>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
-                    : launch_attn_win3<80>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+    return hd == 64 ? launch_attn_win3<64>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, 0, 0, st)
+                    : launch_attn_win3<80>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, 0, 0, st);
   }
   const char* gv = getenv("SAMQ_ATTN_GLOB");  // "v1": first global design (one softmax warpgroup)
   const bool glob_v1 = gv && strcmp(gv, "v1") == 0;
@@ -1930,4 +1943,29 @@ extern "C" int samq_attn_relpos_fwd(const void* qkv, const void* rel_pos_h, cons
   if (glob) return launch_attn<80, false>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
   return win_v1 ? launch_attn<80, true>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st)
                 : launch_attn_win<80>(qkv, rel_pos_h, rel_pos_w, out, B, heads, scale, relw_mode, st);
+}
+
+extern "C" int samq_attn_relpos_unpartition_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w,
+                                                void* out, int B, int H, int W, int ws, int heads, int hd,
+                                                float scale, int relw_mode, void* stream) {
+  using namespace samq;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const char* who = "samq_attn_relpos_unpartition_fwd";
+  SAMQ_REQUIRE(qkv && rel_pos_h && rel_pos_w && out, SAMQ_ERR_BAD_ARG, "%s: null pointer", who);
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(rel_pos_h) |
+                reinterpret_cast<uintptr_t>(rel_pos_w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "%s: pointers must be 16-byte aligned", who);
+  SAMQ_REQUIRE(relw_mode == SAMQ_RELW_REFERENCE || relw_mode == SAMQ_RELW_UPSTREAM, SAMQ_ERR_BAD_ARG,
+               "%s: bad relw_mode %d", who, relw_mode);
+  SAMQ_REQUIRE(ws == 14, SAMQ_ERR_BAD_SHAPE, "%s: window size %d not supported (14)", who, ws);
+  SAMQ_REQUIRE(hd == 64 || hd == 80, SAMQ_ERR_BAD_SHAPE, "%s: head_dim %d not supported (64 or 80)", who, hd);
+  SAMQ_REQUIRE(B > 0 && H > 0 && W > 0 && heads > 0 && heads <= 65535, SAMQ_ERR_BAD_SHAPE,
+               "%s: B=%d H=%d W=%d heads=%d out of range", who, B, H, W, heads);
+  const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
+  const int64_t windows = static_cast<int64_t>(B) * nH * nW;
+  SAMQ_REQUIRE(windows * heads < (1ll << 31), SAMQ_ERR_BAD_SHAPE, "%s: too many (window, head) items", who);
+  return hd == 64 ? launch_attn_win3<64>(qkv, rel_pos_h, rel_pos_w, out, static_cast<int>(windows), heads, scale,
+                                         relw_mode, H, W, st)
+                  : launch_attn_win3<80>(qkv, rel_pos_h, rel_pos_w, out, static_cast<int>(windows), heads, scale,
+                                         relw_mode, H, W, st);
 }

@@ -408,7 +408,7 @@ extern "C" int samq_dense_linear_fwd(const void* x, const void* wt, const void* 
   if (rc != SAMQ_OK) return rc;
   SAMQ_REQUIRE(wt && reinterpret_cast<uintptr_t>(wt) % 16 == 0, SAMQ_ERR_BAD_ARG,
                "samq_dense_linear_fwd: wt must be non-null and 16-byte aligned");
-  const RowMap identity = {0, 0, 0, 0, 0};
+  const RowMap identity = {0, 0, 0, 0, 0, 0};
   return launch_dense(x, wt, reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(residual),
                       reinterpret_cast<__half*>(y), M, K, N, epilogue, identity,
                       reinterpret_cast<cudaStream_t>(stream));
@@ -418,7 +418,7 @@ extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int
                                 const void* scales, const int32_t* g_idx, const void* bias,
                                 const void* residual, void* y, void* workspace, int64_t M, int K,
                                 int N, int bits, int groupsize, int epilogue, void* stream) {
-  const samq::RowMap identity = {0, 0, 0, 0, 0};
+  const samq::RowMap identity = {0, 0, 0, 0, 0, 0};
   return samq::qlinear_impl("samq_qlinear_fwd", x, qweight, qzeros, scales, g_idx, bias, residual, y, workspace,
                             M, K, N, bits, groupsize, epilogue, identity, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -434,7 +434,54 @@ extern "C" int samq_qlinear_unpartition_fwd(const void* x, const int32_t* qweigh
   SAMQ_REQUIRE(shortcut != nullptr, SAMQ_ERR_BAD_ARG, "samq_qlinear_unpartition_fwd: shortcut is required");
   const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
   const int64_t M = static_cast<int64_t>(B) * nH * nW * ws * ws;
-  const RowMap rm = {ws, H, W, nH, nW};
+  const RowMap rm = {ws, H, W, nH, nW, 0};
   return qlinear_impl("samq_qlinear_unpartition_fwd", x, qweight, qzeros, scales, g_idx, bias, shortcut, y,
                       workspace, M, K, N, bits, groupsize, SAMQ_EPI_NONE, rm, reinterpret_cast<cudaStream_t>(stream));
+}
+
+namespace samq {
+namespace {
+
+// qkv rows of the zero-padding tokens of the window layout: x is exactly 0 there, so the reference's
+// GEMM yields fp16(0 + bias) = bias (0 without a bias).  One warp per windowed token.
+__global__ void fill_pad_rows_kernel(__half* __restrict__ y, const __half* __restrict__ bias, int rows, int N,
+                                     RowMap rm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int per_win = rm.ws * rm.ws;
+  const int win = row / per_win, within = row - win * per_win;
+  const int i = within / rm.ws, j = within - i * rm.ws;
+  const int ww = win % rm.nW, wh = (win / rm.nW) % rm.nH;
+  if (wh * rm.ws + i < rm.H && ww * rm.ws + j < rm.W) return;   // a real token: written by the GEMM
+  uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * N);
+  const uint4* src = reinterpret_cast<const uint4*>(bias);
+  for (int c = threadIdx.x & 31; c < N / 8; c += 32) dst[c] = bias ? src[c] : make_uint4(0, 0, 0, 0);
+}
+
+}  // namespace
+}  // namespace samq
+
+extern "C" int samq_qlinear_partition_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,
+                                          const void* scales, const int32_t* g_idx, const void* bias, void* y,
+                                          void* workspace, int B, int H, int W, int ws, int K, int N, int bits,
+                                          int groupsize, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(B > 0 && H > 0 && W > 0 && ws > 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_qlinear_partition_fwd: B=%d H=%d W=%d ws=%d", B, H, W, ws);
+  SAMQ_REQUIRE(N % 8 == 0, SAMQ_ERR_BAD_SHAPE, "samq_qlinear_partition_fwd: N=%d must be a multiple of 8", N);
+  const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
+  const int64_t M_img = static_cast<int64_t>(B) * H * W;
+  const RowMap to_win = {ws, H, W, nH, nW, 1};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = qlinear_impl("samq_qlinear_partition_fwd", x, qweight, qzeros, scales, g_idx, bias, nullptr, y, workspace,
+                        M_img, K, N, bits, groupsize, SAMQ_EPI_NONE, to_win, st);
+  if (rc != SAMQ_OK) return rc;
+  if (nH * ws != H || nW * ws != W) {
+    const int rows = B * nH * nW * ws * ws;
+    fill_pad_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<__half*>(y),
+                                                         reinterpret_cast<const __half*>(bias), rows, N, to_win);
+    count_launch();
+    return check_launch("fill_pad_rows_kernel");
+  }
+  return SAMQ_OK;
 }

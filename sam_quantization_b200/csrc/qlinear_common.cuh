@@ -8,6 +8,8 @@ namespace samq {
 // Defined outside the anonymous namespace: it appears in cross-file launcher signatures.
 struct RowMap {
   int ws, H, W, nH, nW;
+  int to_windows;   // 0: GEMM rows are windowed tokens, stored in image order (pad tokens dropped);
+                    // 1: GEMM rows are image-order tokens, stored at their windowed position
 };
 
 namespace {
@@ -59,6 +61,15 @@ __device__ __forceinline__ uint32_t h2_dup(__half h) {
 __device__ __forceinline__ int map_row(int m, int M, const RowMap& rm) {
   if (m >= M) return -1;
   if (rm.ws == 0) return m;
+  if (rm.to_windows) {
+    // window_partition (image_encoder.py:282-306) fused into the store: token (b, h, w) goes to
+    // window (h / ws, w / ws), position (h % ws, w % ws); the zero-padding rows are not touched
+    const int w = m % rm.W, t = m / rm.W;
+    const int h = t % rm.H, b = t / rm.H;
+    const int wh = h / rm.ws, i = h - wh * rm.ws;
+    const int ww = w / rm.ws, j = w - ww * rm.ws;
+    return (((b * rm.nH + wh) * rm.nW + ww) * rm.ws + i) * rm.ws + j;
+  }
   const int per_win = rm.ws * rm.ws;
   const int win = m / per_win, within = m - win * per_win;
   const int i = within / rm.ws, j = within - i * rm.ws;

@@ -56,12 +56,28 @@ class QuantAttention(nn.Module):
                                self.scale, _RELW[self.relw_mode])
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
-                unpartition_window: int = 0) -> torch.Tensor:
+                unpartition_window: int = 0, partition_window: int = 0) -> torch.Tensor:
         """Input ``[B, H, W, C]`` -> ``[B, H, W, C]`` (fused_attention.py:107-149).
         Additive: ``residual`` is fused into the proj GEMM epilogue; with
         ``unpartition_window = ws`` the input is windowed tokens ``[B*nWin, ws, ws, C]``, and the
         proj epilogue also performs window_unpartition + crop, returning
-        ``residual + unpartition(attn)`` in the residual's ``[B, H, W, C]`` image order."""
+        ``residual + unpartition(attn)`` in the residual's ``[B, H, W, C]`` image order.
+        With ``partition_window = ws`` the input is the UN-partitioned ``[B, H, W, C]``: the qkv GEMM
+        does the window_partition in its store and the attention kernel the window_unpartition in
+        its own, so the zero-padding tokens of the window layout are never multiplied by a weight
+        (as keys they still take part, with q = k = v = bias, exactly like the reference)."""
+        if partition_window:
+            ws = partition_window
+            B, H, W, _ = x.shape
+            qkv = self.qkv_proj.forward_partition(x, ws)
+            if not self.use_rel_pos:
+                raise NotImplementedError      # fused_attention.py:134-135
+            rph, rpw = self.rel_pos_h, self.rel_pos_w
+            if rph.dtype != torch.float16:
+                rph, rpw = rph.half(), rpw.half()
+            o = ops.attn_relpos_unpartition(qkv, rph.contiguous(), rpw.contiguous(), B, H, W, ws, self.num_heads,
+                                            self.scale, _RELW[self.relw_mode])
+            return self.o_proj(o, residual=residual) if residual is not None else self.o_proj(o)
         B, H, W, _ = x.shape
         qkv = self.qkv_proj(x)
         o = self.attention(qkv, B, H, W)

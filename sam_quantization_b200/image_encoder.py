@@ -25,6 +25,7 @@ Patch embedding and neck (0.26 % of FLOPs) stay on cuDNN/ATen.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple, Type
 
 import torch
@@ -213,9 +214,16 @@ class Block(nn.Module):
         n1, n2 = self.norm1, self.norm2
         if self.window_size > 0:
             ws = self.window_size
-            xw, _ = ops.layernorm_partition(x, n1.weight, n1.bias, n1.eps, ws)
             # proj epilogue does window_unpartition + crop + residual: shortcut + unpartition(attn)
-            x = self.attn(xw, residual=x, unpartition_window=ws)
+            if ws == 14 and os.environ.get("SAMQ_PAD_SKIP", "1") != "0":   # "0": partition first, multiply the pad rows
+                # qkv GEMM does the window_partition in its store, the attention kernel the
+                # window_unpartition in its own: the zero-padding tokens (16 % of the window layout
+                # at 64x64 / 14) are neither normalised nor multiplied by qkv / proj weights
+                xn = ops.layernorm(x, n1.weight, n1.bias, n1.eps)
+                x = self.attn(xn, residual=x, partition_window=ws)
+            else:
+                xw, _ = ops.layernorm_partition(x, n1.weight, n1.bias, n1.eps, ws)
+                x = self.attn(xw, residual=x, unpartition_window=ws)
         else:
             xn = ops.layernorm(x, n1.weight, n1.bias, n1.eps)
             x = self.attn(xn, residual=x)                       # residual fused into proj

@@ -123,6 +123,36 @@ def qlinear_unpartition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Te
     return y
 
 
+def qlinear_partition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
+                      bits: int, groupsize: int, bias: Optional[torch.Tensor], window_size: int,
+                      g_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``window_partition(x) @ W + bias`` without multiplying the zero-padding tokens: ``x`` is
+    ``[B, H, W, K]`` (image order); returns ``[B*nWin, ws, ws, N]``, pad rows set to ``bias``."""
+    if bits not in (2, 3, 4, 8):
+        raise NotImplementedError("Only 2, 3, 4 and 8 bits are supported.")
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x")
+    assert x.dim() == 4 and x.is_contiguous()
+    B, H, W, K = x.shape
+    ws = window_size
+    nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
+    N = qweight.shape[1]
+    assert qweight.shape[0] * 32 // bits == K
+    if bias is not None:
+        _check_half(bias, "bias")
+        assert bias.numel() == N
+    M = B * H * W
+    with _dev_ctx(x):
+        y = torch.empty((B * nH * nW, ws, ws, N), dtype=torch.float16, device=x.device)
+        fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
+        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or os.environ.get("SAMQ_GEMM") == "dense"
+        wsp = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
+        _lib.check(_lib.load().samq_qlinear_partition_fwd(
+            _lib.ptr(x), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx), _lib.ptr(bias),
+            _lib.ptr(y), _lib.ptr(wsp), B, H, W, ws, K, N, bits, groupsize, _lib.stream_ptr(x.device)))
+    return y
+
+
 def dense_linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
                  epilogue: int = _lib.EPI_NONE, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``epi(x @ wt.T + bias) + residual`` with ``wt[N, K]`` fp16 (already dequantised)."""
@@ -223,5 +253,28 @@ def attn_relpos(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Ten
         out = torch.empty((B, H, W, num_heads * hd), dtype=torch.float16, device=qkv.device)
         _lib.check(_lib.load().samq_attn_relpos_fwd(
             _lib.ptr(qkv), _lib.ptr(rel_pos_h), _lib.ptr(rel_pos_w), _lib.ptr(out), B, H, W,
+            num_heads, hd, float(scale), relw_mode, _lib.stream_ptr(qkv.device)))
+    return out
+
+
+def attn_relpos_unpartition(qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, B: int, H: int,
+                            W: int, window_size: int, num_heads: int, scale: float,
+                            relw_mode: int = _lib.RELW_REFERENCE) -> torch.Tensor:
+    """Windowed attention + window_unpartition: ``qkv[B*nWin, ws, ws, 3*heads*hd]`` (windowed tokens,
+    zero-padding tokens included) -> ``[B, H, W, heads*hd]`` in image order."""
+    _lib.require_cuda(qkv, "qkv")
+    _check_half(qkv, "qkv"); _check_half(rel_pos_h, "rel_pos_h"); _check_half(rel_pos_w, "rel_pos_w")
+    ws = window_size
+    nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
+    D3 = qkv.shape[-1]
+    assert D3 % (3 * num_heads) == 0
+    hd = D3 // 3 // num_heads
+    assert qkv.numel() == B * nH * nW * ws * ws * D3
+    assert rel_pos_h.shape == (2 * ws - 1, hd) and rel_pos_w.shape == (2 * ws - 1, hd), \
+        "rel_pos tables must be [2*window-1, head_dim] (no interpolation path)"
+    with _dev_ctx(qkv):
+        out = torch.empty((B, H, W, num_heads * hd), dtype=torch.float16, device=qkv.device)
+        _lib.check(_lib.load().samq_attn_relpos_unpartition_fwd(
+            _lib.ptr(qkv), _lib.ptr(rel_pos_h), _lib.ptr(rel_pos_w), _lib.ptr(out), B, H, W, ws,
             num_heads, hd, float(scale), relw_mode, _lib.stream_ptr(qkv.device)))
     return out

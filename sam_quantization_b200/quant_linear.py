@@ -112,6 +112,12 @@ class QuantLinear(nn.Module):
         return ops.qlinear_unpartition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
                                        self.bias, shortcut, window_size, self.g_idx)
 
+    def forward_partition(self, x: torch.Tensor, window_size: int) -> torch.Tensor:
+        """``self(window_partition(x))`` in one kernel: ``x[B, H, W, K]`` in image order ->
+        ``[B*nWin, ws, ws, N]``; the zero-padding tokens are not multiplied (their rows = bias)."""
+        return ops.qlinear_partition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
+                                     self.bias, window_size, self.g_idx)
+
     def dequantize(self, transposed: bool = False) -> torch.Tensor:
         """fp16 ``W[K, N]`` (``[N, K]`` if transposed) via ``samq_unpack_dequant``."""
         return ops.unpack_dequant(self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,

@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(w, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(b, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
   cudaMemset(res, 0, static_cast<size_t>(M) * N * 2);
-  samq::RowMap rm{0, 0, 0, 0, 0};
+  samq::RowMap rm{0, 0, 0, 0, 0, 0};
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 4; ++it) {
     cudaEventRecord(e0);

@@ -65,6 +65,28 @@ def test_ablation_kernels_agree_with_default(cuda_device, monkeypatch, env, val,
     assert (new.float() - old.float()).abs().max().item() <= 1e-3
 
 
+@pytest.mark.parametrize("B,H,W,heads,hd", [(2, 64, 64, 16, 80), (1, 64, 64, 12, 64), (3, 20, 30, 2, 80),
+                                            (1, 14, 14, 3, 64), (2, 9, 40, 2, 80)])
+@pytest.mark.parametrize("relw", [0, 1])
+def test_windowed_attention_with_fused_unpartition(cuda_device, B, H, W, heads, hd, relw):
+    """samq_attn_relpos_unpartition_fwd == window_unpartition(samq_attn_relpos_fwd(windows)) bit for
+    bit (image_encoder.py:309-333): each window tile leaves as one TMA box placed at the window's
+    position in the image, and the box elements outside the image are not written."""
+    ws = 14
+    nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
+    Bw = B * nH * nW
+    qkv, rph, rpw = make_inputs(Bw, ws, heads, hd, seed=13)
+    qkv_d, rph_d, rpw_d = qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device)
+    win = ops.attn_relpos(qkv_d, rph_d, rpw_d, Bw, ws, ws, heads, hd ** -0.5, relw)
+    out = torch.full((B, H, W, heads * hd), float("nan"), dtype=torch.float16, device=cuda_device)
+    img = ops.attn_relpos_unpartition(qkv_d.view(Bw, ws, ws, -1), rph_d, rpw_d, B, H, W, ws, heads, hd ** -0.5, relw)
+    ref = oe.window_unpartition(win.float().cpu(), ws, (nH * ws, nW * ws), (H, W)).half()
+    assert img.shape == (B, H, W, heads * hd)
+    assert not torch.isnan(img).any()
+    assert torch.equal(img.cpu(), ref)
+    del out
+
+
 def test_relw_modes_differ(cuda_device):
     qkv, rph, rpw = make_inputs(2, 14, 2, 64)
     a = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), 2, 14, 14, 2, 0.125, 0)

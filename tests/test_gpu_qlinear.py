@@ -205,3 +205,31 @@ def test_proj_with_fused_unpartition_and_residual(cuda_device, monkeypatch, B, H
     err, mag, cos = report(y, ref)
     assert y.shape == (B, H, W, N)
     assert err <= 2 * ULP * mag and cos >= 0.99999
+
+
+@pytest.mark.parametrize("B,H,W,K,N,variant", [(3, 64, 64, 1280, 3840, "auto"), (1, 64, 64, 256, 768, "auto"),
+                                               (2, 20, 30, 128, 384, "auto"), (2, 28, 28, 128, 256, "auto"),
+                                               (3, 64, 64, 256, 768, "dense"), (2, 64, 64, 256, 768, "2cta")])
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_qkv_with_fused_partition(cuda_device, monkeypatch, B, H, W, K, N, variant, with_bias):
+    """samq_qlinear_partition_fwd == window_partition(x) @ W + bias (image_encoder.py:196-198,
+    282-306) on every GEMM kernel variant -- bit-identical to partitioning first, because the real
+    rows see the same dot products and a zero-padding row's result is exactly fp16(0 + bias)."""
+    from oracle import encoder as oe
+    if variant == "auto":
+        monkeypatch.delenv("SAMQ_GEMM", raising=False)
+    else:
+        monkeypatch.setenv("SAMQ_GEMM", variant)
+    ws = 14
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=44)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, H, W, K, generator=g).half()
+    b = torch.randn(N, generator=g).half() if with_bias else None
+    packed = (dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device), 4, 128)
+    bd = b.to(cuda_device) if with_bias else None
+    y = ops.qlinear_partition(x.to(cuda_device), *packed, bd, ws)
+    xw, _ = oe.window_partition(x.float(), ws)
+    xw = xw.half().contiguous()
+    ref = ops.qlinear(xw.to(cuda_device), *packed, bd)
+    assert y.shape == ref.shape
+    assert torch.equal(y, ref)
