@@ -70,6 +70,11 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float ex2v(float x) {   // volatile: keeps its place among other volatile asm
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -1745,20 +1750,33 @@ attn_glob_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid_
       // ---- P = 2^(x - m) -> P columns [32g, 32g + 32) of the tile's S buffer.  Warpgroup 1's P
       // columns overlap warpgroup 0's S columns [32, 64): all S reads of this tile completed one
       // iteration ago (prefetch), before the barrier above. ----
+      // Each group of four ex2 is followed in the source by the scale / bias / max arithmetic of
+      // four scores of the NEXT tile: a warp issues in order and the MUFU pipe takes one
+      // warp-instruction per 8 clk, so FMA work placed between the ex2 (instead of behind all 64)
+      // overlaps with it.  ptxas keeps about half of the interleave (1076 -> 1046 us).
       uint32_t pk[32];
-      float sum0 = 0.f, sum1 = 0.f;
+      float sum0 = 0.f, sum1 = 0.f, a0 = -INFINITY, a1 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
-        const float p0 = ex2(x[i + 0] - mm), p1 = ex2(x[i + 1] - mm);
-        const float p2 = ex2(x[i + 2] - mm), p3 = ex2(x[i + 3] - mm);
+        const float p0 = ex2v(x[i + 0] - mm), p1 = ex2v(x[i + 1] - mm);
+        const float p2 = ex2v(x[i + 2] - mm), p3 = ex2v(x[i + 3] - mm);
         sum0 += p0 + p2;
         sum1 += p1 + p3;
         pk[(i >> 1) + 0] = pack_h2(p0, p1);
         pk[(i >> 1) + 1] = pack_h2(p2, p3);
+        if (more) {
+          const float4 w = ld_bw((i >> 2) & 7, i >> 5);
+          nx[i + 0] = fmaf(nx[i + 0], c_scale, w.x);
+          nx[i + 1] = fmaf(nx[i + 1], c_scale, w.y);
+          nx[i + 2] = fmaf(nx[i + 2], c_scale, w.z);
+          nx[i + 3] = fmaf(nx[i + 3], c_scale, w.w);
+          a0 = fmaxf(a0, fmaxf(nx[i + 0], nx[i + 2]));
+          a1 = fmaxf(a1, fmaxf(nx[i + 1], nx[i + 3]));
+        }
       }
       l += sum0 + sum1;
+      if (more) mx_raw = fmaxf(a0, a1);
       tmem_st_x32(tmem_base + 128 * buf + lane_off + 32 * g, pk);
-      if (more) mx_raw = bias_max(nx);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
