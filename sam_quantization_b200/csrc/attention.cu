@@ -1458,6 +1458,18 @@ attn_glob_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid_
     mbar_init(&pv_done[1], 1);
     fence_barrier_init();
   }
+  if (warp == 8 && lane == 0) {
+    // descriptor fetch overlaps barrier init / TMEM allocation (first-load latency is on the
+    // critical path of this one-item CTA)
+    tma_prefetch_desc(&map_qkv_main);
+    tma_prefetch_desc(&map_rph_main);
+    tma_prefetch_desc(&map_rpw_main);
+    if (C::kTail) {
+      tma_prefetch_desc(&map_qkv_tail);
+      tma_prefetch_desc(&map_rph_tail);
+      tma_prefetch_desc(&map_rpw_tail);
+    }
+  }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
