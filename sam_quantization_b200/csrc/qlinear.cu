@@ -443,19 +443,31 @@ namespace samq {
 namespace {
 
 // qkv rows of the zero-padding tokens of the window layout: x is exactly 0 there, so the reference's
-// GEMM yields fp16(0 + bias) = bias (0 without a bias).  One warp per windowed token.
+// GEMM yields fp16(0 + bias) = bias (0 without a bias).  A warp owns 32 consecutive windowed tokens:
+// one lane per token decides "padding?", then the whole warp copies the bias into each flagged row
+// (the first version launched a warp per token, 39200 of them for 6432 rows to write).
 __global__ void fill_pad_rows_kernel(__half* __restrict__ y, const __half* __restrict__ bias, int rows, int N,
                                      RowMap rm) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int per_win = rm.ws * rm.ws;
-  const int win = row / per_win, within = row - win * per_win;
-  const int i = within / rm.ws, j = within - i * rm.ws;
-  const int ww = win % rm.nW, wh = (win / rm.nW) % rm.nH;
-  if (wh * rm.ws + i < rm.H && ww * rm.ws + j < rm.W) return;   // a real token: written by the GEMM
-  uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * N);
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (row0 >= rows) return;
+  const int row = row0 + lane;
+  bool pad = false;
+  if (row < rows) {
+    const int per_win = rm.ws * rm.ws;
+    const int win = row / per_win, within = row - win * per_win;
+    const int i = within / rm.ws, j = within - i * rm.ws;
+    const int ww = win % rm.nW, wh = (win / rm.nW) % rm.nH;
+    pad = !(wh * rm.ws + i < rm.H && ww * rm.ws + j < rm.W);
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, pad);
   const uint4* src = reinterpret_cast<const uint4*>(bias);
-  for (int c = threadIdx.x & 31; c < N / 8; c += 32) dst[c] = bias ? src[c] : make_uint4(0, 0, 0, 0);
+  while (mask) {
+    const int r = __ffs(mask) - 1;
+    mask &= mask - 1;
+    uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * N);
+    for (int c = lane; c < N / 8; c += 32) dst[c] = bias ? src[c] : make_uint4(0, 0, 0, 0);
+  }
 }
 
 }  // namespace
@@ -478,7 +490,7 @@ extern "C" int samq_qlinear_partition_fwd(const void* x, const int32_t* qweight,
   if (rc != SAMQ_OK) return rc;
   if (nH * ws != H || nW * ws != W) {
     const int rows = B * nH * nW * ws * ws;
-    fill_pad_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(reinterpret_cast<__half*>(y),
+    fill_pad_rows_kernel<<<(rows + 255) / 256, 256, 0, st>>>(reinterpret_cast<__half*>(y),
                                                          reinterpret_cast<const __half*>(bias), rows, N, to_win);
     count_launch();
     return check_launch("fill_pad_rows_kernel");
