@@ -110,3 +110,18 @@ def test_pad_skipping_block_is_bit_identical(cuda_device, tmp_path, monkeypatch,
         monkeypatch.setenv("SAMQ_PAD_SKIP", "1")
         new = enc.forward_tokens(x)
     assert torch.equal(old, new)
+
+
+def test_vit_l_width_blocks_batched(cuda_device, tmp_path):
+    """BASELINE config 2 shapes (ViT-L: dim 1024, 16 heads of 64, batch > 1 so that the GEMMs take
+    the unpack-once + CTA-pair path and the windowed block its pad-skipping form), two blocks
+    (windowed + global) against the oracle.  Parity unpinned by reference for batch > 1."""
+    cfg = dict(embed_dim=1024, depth=2, num_heads=16, global_attn_indexes=(1,))
+    enc, ref_state = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=21, device=cuda_device)
+    x = torch.from_numpy(synth.tokens_input(3, 64, 1024, seed=22)).half()
+    with torch.no_grad():
+        y = enc.forward_tokens(x.to(cuda_device))
+        ref = oe.tokens_forward(x.float(), ref_state, 2, 16, 14, (1,), "reference")
+    err, mag, cos = report(y, ref)
+    print(f"ViT-L width, batch 3: max-abs {err:.3e} (max|ref| {mag:.3f}) cosine {cos:.7f}")
+    assert err <= 1.5e-2 * mag and cos >= 0.9999
