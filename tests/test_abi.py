@@ -11,6 +11,15 @@ from sam_quantization_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(scope="module", autouse=True)
+def built_library():
+    """A fresh checkout has no libsamq.so (build artefacts are git-ignored): build it (nvcc
+    cross-compiles sm_100a without a GPU) instead of failing on a missing file."""
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "samq.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
