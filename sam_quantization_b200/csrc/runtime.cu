@@ -79,6 +79,7 @@ struct MapKeyHash {
 
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap*, MapKeyHash> g_maps;
+static std::vector<CUtensorMap*> g_retired;
 
 const CUtensorMap* get_tensor_map_nd(const void* base, int rank, const uint64_t* dims,
                                      const uint64_t* strides_bytes, const uint32_t* box,
@@ -138,9 +139,13 @@ const CUtensorMap* get_tensor_map_nd(const void* base, int rank, const uint64_t*
     free(mem);
     return nullptr;
   }
-  // bound the cache: descriptors are tiny, but activation pointers may churn
+  // bound the cache: descriptors are tiny, but activation pointers may churn.  Evicted
+  // descriptors are freed one generation late: a caller on another thread may still be between
+  // "got the pointer" and "passed *map by value to its launch".
   if (g_maps.size() > 16384) {
-    for (auto& kv : g_maps) free(kv.second);
+    for (CUtensorMap* m : g_retired) free(m);
+    g_retired.clear();
+    for (auto& kv : g_maps) g_retired.push_back(kv.second);
     g_maps.clear();
   }
   g_maps.emplace(key, map);
