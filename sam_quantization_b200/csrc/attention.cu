@@ -784,15 +784,7 @@ int launch_attn_win(const void* qkv, const void* rph, const void* rpw, void* out
     if (!mqt || !mkvt || !mht || !mwt) return SAMQ_ERR_LAUNCH;
   }
   auto kern = attn_win_kernel<HD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn_win smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "attn_win"); rc != SAMQ_OK) return rc;
   dim3 grid(2, heads, B);
   kern<<<grid, kAttThreads, C::kSmemBytes, st>>>(*mq, *mqt, *mkv, *mkvt, *mh, *mht, *mw, *mwt,
                                                 reinterpret_cast<__half*>(out), heads, scale, relw_mode);
@@ -1321,19 +1313,8 @@ int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* ou
     if (!mqat || !mqbt || !mkvt || !mht || !mwt) return SAMQ_ERR_LAUNCH;
   }
   auto kern = attn_win3_kernel<HD>;
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn_win3 smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "attn_win3"); rc != SAMQ_OK) return rc;
+  const int num_sms = device_sm_count();
   const int n_items = B * heads;
   dim3 grid(n_items < num_sms ? n_items : num_sms);
   kern<<<grid, kWin3Threads, C::kSmemBytes, st>>>(*mqa, *mqat, *mqb, *mqbt, *mkv, *mkvt, *mh, *mht, *mw, *mwt, *moa, *mob,
@@ -1873,15 +1854,7 @@ int launch_attn_glob(const void* qkv, const void* rph, const void* rpw, void* ou
     if (!m_tail || !h_tail || !w_tail) return SAMQ_ERR_LAUNCH;
   }
   auto kern = attn_glob_kernel<HD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn_glob smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "attn_glob"); rc != SAMQ_OK) return rc;
   dim3 grid(C::kQTiles, heads, B);
   kern<<<grid, kGlobThreads, C::kSmemBytes, st>>>(*m_main, *m_tail, *h_main, *h_tail, *w_main, *w_tail,
                                                  reinterpret_cast<__half*>(out), heads, scale, relw_mode);
@@ -1915,15 +1888,7 @@ int launch_attn(const void* qkv, const void* rph, const void* rpw, void* out, in
     if (!m_tail || !h_tail || !w_tail) return SAMQ_ERR_LAUNCH;
   }
   auto kern = attn_relpos_kernel<HD, WIN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(attn smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "attn"); rc != SAMQ_OK) return rc;
   dim3 grid(C::kQTiles, heads, B);
   kern<<<grid, kAttThreads, C::kSmemBytes, st>>>(*m_main, *m_tail, *h_main, *h_tail, *w_main, *w_tail,
                                                 reinterpret_cast<__half*>(out), heads, scale, relw_mode);

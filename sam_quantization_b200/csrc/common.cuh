@@ -32,6 +32,9 @@ int check_launch(const char* what);  // cudaGetLastError -> status
 const CUtensorMap* get_tensor_map_2d(const void* base, uint64_t rows, uint64_t cols,
                                      uint64_t row_stride_bytes, uint32_t box_rows,
                                      uint32_t box_cols, int elem_bytes, int swizzle);
+// per-device, once: raise the dynamic shared-memory limit of a kernel; SM count of the current device
+int ensure_dynamic_smem(const void* func, int bytes, const char* what);
+int device_sm_count();
 // generic N-d (<=5) map, dims innermost first; strides in bytes for dims 1..n-1
 const CUtensorMap* get_tensor_map_nd(const void* base, int rank, const uint64_t* dims,
                                      const uint64_t* strides_bytes, const uint32_t* box,

@@ -273,16 +273,7 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   }
 }
 
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+int num_sms() { return device_sm_count(); }
 
 template <int BM, bool FUSED>
 int launch_qlinear(const void* x, const void* w, const __half* scales, const int32_t* qzeros,
@@ -296,15 +287,7 @@ int launch_qlinear(const void* x, const void* w, const __half* scales, const int
             : get_tensor_map_2d(w, N, K, static_cast<uint64_t>(K) * 2, kBN, kBK, 2, 3);
   if (!mw) return SAMQ_ERR_LAUNCH;
   auto kern = epilogue == SAMQ_EPI_GELU ? qlinear_kernel<BM, FUSED, true> : qlinear_kernel<BM, FUSED, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[epilogue == SAMQ_EPI_GELU]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    attr_set[epilogue == SAMQ_EPI_GELU] = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "qlinear_kernel"); rc != SAMQ_OK) return rc;
   const int NT = N / kBN;
   const int64_t MT = (M + BM - 1) / BM;
   const int64_t tiles = NT * MT;

@@ -255,15 +255,7 @@ int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales
   if (!mx || !mw) return SAMQ_ERR_LAUNCH;
   const bool gelu = epilogue == SAMQ_EPI_GELU;
   auto kern = gelu ? qlinear2_kernel<BM, true> : qlinear2_kernel<BM, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[gelu]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(qlinear2 smem=%d): %s", C::kSmemBytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    attr_set[gelu] = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "qlinear2_kernel"); rc != SAMQ_OK) return rc;
   const int NT = N / (2 * kBN2);
   const int64_t MT = (M + BM - 1) / BM;
   const int64_t tiles = NT * MT;

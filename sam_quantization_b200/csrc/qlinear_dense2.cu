@@ -248,17 +248,8 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
   const bool res = residual != nullptr;
   auto kern = gelu ? (res ? dense2_kernel<true, true> : dense2_kernel<true, false>)
                    : (res ? dense2_kernel<false, true> : dense2_kernel<false, false>);
-  static bool attr_set[4] = {false, false, false, false};
-  const int variant = (gelu ? 2 : 0) + (res ? 1 : 0);
   const int smem_bytes = gelu ? kDSmemBytes<true> : kDSmemBytes<false>;
-  if (!attr_set[variant]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(dense2 smem=%d): %s", smem_bytes, cudaGetErrorString(e));
-      return SAMQ_ERR_LAUNCH;
-    }
-    attr_set[variant] = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes, "dense2_kernel"); rc != SAMQ_OK) return rc;
   const int NT = N / (2 * kDBN);
   const int64_t MT = (M + kDBM - 1) / kDBM;
   const int64_t tiles = NT * MT;

@@ -152,6 +152,40 @@ const CUtensorMap* get_tensor_map_nd(const void* base, int rank, const uint64_t*
   return map;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per DEVICE: a process that
+// drives several GPUs must not reuse what it set / read for the first one.
+int ensure_dynamic_smem(const void* func, int bytes, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> done;     // (function, device) -> bytes set
+  const uint64_t key = reinterpret_cast<uint64_t>(func) * 64 + static_cast<uint64_t>(dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return SAMQ_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%s, smem=%d): %s", what, bytes, cudaGetErrorString(e));
+    return SAMQ_ERR_LAUNCH;
+  }
+  done[key] = bytes;
+  return SAMQ_OK;
+}
+
+int device_sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static std::mutex mu;
+  static int cached[64] = {0};
+  std::lock_guard<std::mutex> lock(mu);
+  int& n = cached[dev & 63];
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 const CUtensorMap* get_tensor_map_2d(const void* base, uint64_t rows, uint64_t cols,
                                      uint64_t row_stride_bytes, uint32_t box_rows,
                                      uint32_t box_cols, int elem_bytes, int swizzle) {
