@@ -859,7 +859,7 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
                  const __grid_constant__ CUtensorMap map_o_a, const __grid_constant__ CUtensorMap map_o_b,
                  int heads, int n_items, float scale, int relw_mode, int img_nh, int img_nw) {
   using C = W3Cfg<HD>;
-  constexpr int E = C::E, S = C::S, SP = C::SP;
+  constexpr int E = C::E, SP = C::SP;
   PROF_DECL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
