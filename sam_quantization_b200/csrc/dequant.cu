@@ -131,6 +131,9 @@ __global__ void __launch_bounds__(256)
 dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
                            const __half* __restrict__ scales, __half* __restrict__ wt, int K, int N,
                            int groupsize) {
+  // programmatic dependent launch: the GEMM that consumes Wt may be scheduled right away; it
+  // blocks in griddepcontrol.wait (after its barrier / TMEM set-up) until this grid has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int kblocks = K >> 6;                          // 64-k blocks

@@ -12,6 +12,8 @@
 // 208 B/clk against the ~128 B/clk an SM provides, which capped it at ~65 % of the tensor peak.
 #include "qlinear_common.cuh"
 
+#include <cstdlib>
+
 namespace samq {
 namespace {
 
@@ -107,6 +109,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  // launched with programmatic stream serialization: everything above overlapped the tail of the
+  // preceding kernel (the weight unpack); its results are visible after this wait
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lead_full = mapa_u32(smem_u32(full), 0);
   const uint32_t lead_acc_empty = mapa_u32(smem_u32(acc_empty), 0);
@@ -260,13 +265,19 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
   cfg.blockDim = dim3(gelu ? DCfg<true>::kThreads : DCfg<false>::kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = [] {
+    const char* v = getenv("SAMQ_PDL");
+    return !(v && v[0] == '0');
+  }();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *mx, *mw, bias, residual, y, static_cast<int>(M), N, K, rowmap);
   count_launch();
   if (e != cudaSuccess) {
