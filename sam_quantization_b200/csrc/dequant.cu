@@ -133,7 +133,7 @@ dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* _
                            int groupsize) {
   // programmatic dependent launch: the GEMM that consumes Wt may be scheduled right away; it
   // blocks in griddepcontrol.wait (after its barrier / TMEM set-up) until this grid has completed
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int kblocks = K >> 6;                          // 64-k blocks
@@ -167,6 +167,8 @@ dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* _
     asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(out[4 * r + 2]) : "r"(q4[0]), "r"(q4[1]));
     asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(out[4 * r + 3]) : "r"(q4[2]), "r"(q4[3]));
   }
+  // (the packed weights are constant; the scratch Wt may still be read by an earlier GEMM)
+  pdl_wait();
   uint4* dst = reinterpret_cast<uint4*>(wt + static_cast<int64_t>(n) * K + k0);
   dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
   dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
@@ -204,7 +206,7 @@ int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* sc
   __half* w = reinterpret_cast<__half*>(w_out);
   if (bits == 4 && transposed && g_idx == nullptr && K % 64 == 0 && N % 8 == 0 && groupsize % 16 == 0) {
     const int warps = (N / 8) * (K / 64);
-    dequant4_transposed_kernel<<<(warps + 7) / 8, 256, 0, st>>>(qweight, qzeros, s, w, K, N, groupsize);
+    launch_pdl(1, dequant4_transposed_kernel, dim3((warps + 7) / 8), dim3(256), 0, st, qweight, qzeros, s, w, K, N, groupsize);
     count_launch();
     return check_launch("dequant4_transposed_kernel");
   }

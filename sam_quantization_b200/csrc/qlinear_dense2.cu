@@ -65,6 +65,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
               const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N, int K,
               const RowMap rowmap) {
   GP_DECL;
+  pdl_trigger();   // the next kernel may be scheduled; it waits for this grid's completion itself
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -111,7 +112,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   tc_fence_after();
   // launched with programmatic stream serialization: everything above overlapped the tail of the
   // preceding kernel (the weight unpack); its results are visible after this wait
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lead_full = mapa_u32(smem_u32(full), 0);
   const uint32_t lead_acc_empty = mapa_u32(smem_u32(acc_empty), 0);
@@ -272,12 +273,8 @@ int launch_dense_pair(const void* x, const void* wt, const __half* bias, const _
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  static const bool pdl = [] {
-    const char* v = getenv("SAMQ_PDL");
-    return !(v && v[0] == '0');
-  }();
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *mx, *mw, bias, residual, y, static_cast<int>(M), N, K, rowmap);
   count_launch();
   if (e != cudaSuccess) {

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -170,6 +171,14 @@ int ensure_dynamic_smem(const void* func, int bytes, const char* what) {
   }
   done[key] = bytes;
   return SAMQ_OK;
+}
+
+bool pdl_enabled(int which) {
+  static const int mask = [] {
+    const char* v = getenv("SAMQ_PDL");     // bit mask of kernel classes launched programmatically
+    return v ? atoi(v) : 0x3;
+  }();
+  return (mask >> which) & 1;
 }
 
 int device_sm_count() {
