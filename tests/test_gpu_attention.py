@@ -68,10 +68,11 @@ def test_ablation_kernels_agree_with_default(cuda_device, monkeypatch, env, val,
 @pytest.mark.parametrize("B,H,W,heads,hd", [(2, 64, 64, 16, 80), (1, 64, 64, 12, 64), (3, 20, 30, 2, 80),
                                             (1, 14, 14, 3, 64), (2, 9, 40, 2, 80)])
 @pytest.mark.parametrize("relw", [0, 1])
-def test_windowed_attention_with_fused_unpartition(cuda_device, B, H, W, heads, hd, relw):
+def test_windowed_attention_with_fused_unpartition(cuda_device, monkeypatch, B, H, W, heads, hd, relw):
     """samq_attn_relpos_unpartition_fwd == window_unpartition(samq_attn_relpos_fwd(windows)) bit for
     bit (image_encoder.py:309-333): each window tile leaves as one TMA box placed at the window's
     position in the image, and the box elements outside the image are not written."""
+    monkeypatch.delenv("SAMQ_ATTN_WIN", raising=False)   # both sides on the same (default) kernel
     ws = 14
     nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
     Bw = B * nH * nW
