@@ -52,7 +52,7 @@ def test_windowed_item_scheduling(cuda_device, B, heads, hd):
 
 
 @pytest.mark.parametrize("env,val,B,E", [("SAMQ_ATTN_WIN", "v2", 25, 14), ("SAMQ_ATTN_WIN", "v1", 25, 14),
-                                         ("SAMQ_ATTN_GLOB", "v1", 1, 64)])
+                                         ("SAMQ_ATTN_GLOB", "v1", 1, 64), ("SAMQ_ATTN_GLOB", "v2", 1, 64)])
 def test_ablation_kernels_agree_with_default(cuda_device, monkeypatch, env, val, B, E):
     """The earlier kernel designs stay selectable (SAMQ_ATTN_WIN=v1|v2, SAMQ_ATTN_GLOB=v1) for
     A/B timing; they must compute the same function."""
