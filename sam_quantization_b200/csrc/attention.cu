@@ -857,7 +857,7 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
                  const __grid_constant__ CUtensorMap map_rph_main, const __grid_constant__ CUtensorMap map_rph_tail,
                  const __grid_constant__ CUtensorMap map_rpw_main, const __grid_constant__ CUtensorMap map_rpw_tail,
                  const __grid_constant__ CUtensorMap map_o_a, const __grid_constant__ CUtensorMap map_o_b,
-                 int heads, int n_items, float scale, int relw_mode, int img_nh, int img_nw) {
+                 int heads, int n_items, float scale, int relw_mode, int img_nh, int img_nw, int exact_max) {
   using C = W3Cfg<HD>;
   constexpr int E = C::E, SP = C::SP;
   PROF_DECL;
@@ -1052,6 +1052,8 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
       float bh[E], bw[E];
 #pragma unroll
       for (int k = 0; k < E; ++k) bh[k] = bw[k] = 0.f;
+      float bw_hi = 0.f;
+      bool bound_ok = false;
       PROF_BEGIN;
       mbar_wait(&t_full[X], pn);
       PROF_END(0);
@@ -1101,6 +1103,15 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
           bh[k] = kLog2e * __half2float(__float2half_rn(bh[k]));
           bw[k] = kLog2e * __half2float(__float2half_rn(bw[k]));
         }
+        // see attn_glob3_kernel: where the 14 column biases of every row of this warp lie within
+        // 15 (log2 units) of each other the row maximum is replaced by the bound
+        // max_k(scale * s + bh) + max(bw) - min(spread, 7), which needs no per-element FMA
+        float bw_lo = bw[0];
+        bw_hi = bw[0];
+#pragma unroll
+        for (int k = 1; k < E; ++k) { bw_hi = fmaxf(bw_hi, bw[k]); bw_lo = fminf(bw_lo, bw[k]); }
+        bound_ok = __all_sync(0xffffffffu, !valid || bw_hi - bw_lo <= 15.f) && !exact_max;
+        bw_hi -= fminf(bw_hi - bw_lo, 7.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -1126,23 +1137,51 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
         uint32_t ra[32], rb[32];
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
         tmem_ld_x32(region, ra);
+        if (bound_ok) {
 #pragma unroll 1
-        for (int ii = 0; ii < 4; ++ii) {
+          for (int ii = 0; ii < 4; ++ii) {
 #pragma unroll
-          for (int sb = 0; sb < 2; ++sb) {
-            const int i = 2 * ii + sb;
-            if (i < 7) {
-              uint32_t (&r)[32] = sb ? rb : ra;
-              tmem_ld_wait();
-              if (i < 6) tmem_ld_x32(region + 28 * (i + 1), sb ? ra : rb);
-              const float ba = ii < 2 ? (ii == 0 ? bh[2 * sb] : bh[4 + 2 * sb]) : (ii == 2 ? bh[8 + 2 * sb] : bh[12]);   // ii == 3: only step 6 exists
-              const float bb = ii < 2 ? (ii == 0 ? bh[1 + 2 * sb] : bh[5 + 2 * sb]) : (ii == 2 ? bh[9 + 2 * sb] : bh[13]);
+            for (int sb = 0; sb < 2; ++sb) {
+              const int i = 2 * ii + sb;
+              if (i < 7) {
+                uint32_t (&r)[32] = sb ? rb : ra;
+                tmem_ld_wait();
+                if (i < 6) tmem_ld_x32(region + 28 * (i + 1), sb ? ra : rb);
+                const float ba = ii < 2 ? (ii == 0 ? bh[2 * sb] : bh[4 + 2 * sb]) : (ii == 2 ? bh[8 + 2 * sb] : bh[12]);
+                const float bb = ii < 2 ? (ii == 0 ? bh[1 + 2 * sb] : bh[5 + 2 * sb]) : (ii == 2 ? bh[9 + 2 * sb] : bh[13]);
+                float ua = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+                float ub = fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15]));
 #pragma unroll
-              for (int j = 0; j < 28; j += 4) {
-                m0 = fmaxf(m0, fmaf(__uint_as_float(r[j + 0]), c_scale, bw[(j + 0) % E]) + ((j + 0) >= E ? bb : ba));
-                m1 = fmaxf(m1, fmaf(__uint_as_float(r[j + 1]), c_scale, bw[(j + 1) % E]) + ((j + 1) >= E ? bb : ba));
-                m2 = fmaxf(m2, fmaf(__uint_as_float(r[j + 2]), c_scale, bw[(j + 2) % E]) + ((j + 2) >= E ? bb : ba));
-                m3 = fmaxf(m3, fmaf(__uint_as_float(r[j + 3]), c_scale, bw[(j + 3) % E]) + ((j + 3) >= E ? bb : ba));
+                for (int j = 2; j < E; j += 2) {
+                  ua = fmaxf(fmaxf(ua, __uint_as_float(r[j])), __uint_as_float(r[j + 1]));
+                  ub = fmaxf(fmaxf(ub, __uint_as_float(r[E + j])), __uint_as_float(r[E + j + 1]));
+                }
+                m0 = fmaxf(m0, fmaf(ua, c_scale, ba));
+                m1 = fmaxf(m1, fmaf(ub, c_scale, bb));
+              }
+            }
+          }
+          m0 += bw_hi;
+          m1 += bw_hi;
+        } else {
+  #pragma unroll 1
+          for (int ii = 0; ii < 4; ++ii) {
+  #pragma unroll
+            for (int sb = 0; sb < 2; ++sb) {
+              const int i = 2 * ii + sb;
+              if (i < 7) {
+                uint32_t (&r)[32] = sb ? rb : ra;
+                tmem_ld_wait();
+                if (i < 6) tmem_ld_x32(region + 28 * (i + 1), sb ? ra : rb);
+                const float ba = ii < 2 ? (ii == 0 ? bh[2 * sb] : bh[4 + 2 * sb]) : (ii == 2 ? bh[8 + 2 * sb] : bh[12]);   // ii == 3: only step 6 exists
+                const float bb = ii < 2 ? (ii == 0 ? bh[1 + 2 * sb] : bh[5 + 2 * sb]) : (ii == 2 ? bh[9 + 2 * sb] : bh[13]);
+  #pragma unroll
+                for (int j = 0; j < 28; j += 4) {
+                  m0 = fmaxf(m0, fmaf(__uint_as_float(r[j + 0]), c_scale, bw[(j + 0) % E]) + ((j + 0) >= E ? bb : ba));
+                  m1 = fmaxf(m1, fmaf(__uint_as_float(r[j + 1]), c_scale, bw[(j + 1) % E]) + ((j + 1) >= E ? bb : ba));
+                  m2 = fmaxf(m2, fmaf(__uint_as_float(r[j + 2]), c_scale, bw[(j + 2) % E]) + ((j + 2) >= E ? bb : ba));
+                  m3 = fmaxf(m3, fmaf(__uint_as_float(r[j + 3]), c_scale, bw[(j + 3) % E]) + ((j + 3) >= E ? bb : ba));
+                }
               }
             }
           }
@@ -1275,6 +1314,13 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
   }
 }
 
+// SAMQ_ATTN_MAX=exact (developer switch, A/B timing and tests): the softmax warps take the exact
+// row maximum even where the bound on it would do.
+static int exact_max_requested() {
+  const char* v = getenv("SAMQ_ATTN_MAX");
+  return v && !strcmp(v, "exact");
+}
+
 template <int HD>
 int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* out, int B, int heads, float scale,
                      int relw_mode, int img_h, int img_w, cudaStream_t st) {
@@ -1318,7 +1364,7 @@ int launch_attn_win3(const void* qkv, const void* rph, const void* rpw, void* ou
   const int n_items = B * heads;
   dim3 grid(n_items < num_sms ? n_items : num_sms);
   kern<<<grid, kWin3Threads, C::kSmemBytes, st>>>(*mqa, *mqat, *mqb, *mqbt, *mkv, *mkvt, *mh, *mht, *mw, *mwt, *moa, *mob,
-                                                 heads, n_items, scale, relw_mode, img_nh, img_nw);
+                                                 heads, n_items, scale, relw_mode, img_nh, img_nw, exact_max_requested());
   count_launch();
   return check_launch("attn_win3_kernel");
 }
@@ -1904,7 +1950,7 @@ __global__ void __launch_bounds__(kGlob3Threads, 2)
 attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid_constant__ CUtensorMap map_qkv_tail,
                   const __grid_constant__ CUtensorMap map_rph_main, const __grid_constant__ CUtensorMap map_rph_tail,
                   const __grid_constant__ CUtensorMap map_rpw_main, const __grid_constant__ CUtensorMap map_rpw_tail,
-                  __half* __restrict__ out, int heads, float scale, int relw_mode) {
+                  __half* __restrict__ out, int heads, float scale, int relw_mode, int exact_max) {
   using C = G3Cfg<HD>;
   constexpr int E = C::E, S = C::S, T = C::kKVTiles;
   extern __shared__ uint8_t smem_raw[];
@@ -2096,6 +2142,16 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
     named_bar_sync(1, 128);                 // every row's bh column is visible to its own thread: not
                                             // needed for correctness (own row only) but keeps the
                                             // warps together for the first tile
+    float bw_max = bw[0], bw_min = bw[0];
+#pragma unroll
+    for (int kw = 1; kw < E; ++kw) { bw_max = fmaxf(bw_max, bw[kw]); bw_min = fminf(bw_min, bw[kw]); }
+    // The true tile maximum lies in [bound - spread, bound], spread = max(bw) - min(bw).  Using
+    // bound - min(spread, 7) as the maximum keeps every 2^(x - m) <= 2^(7 + 8 lazy-rescale lag) (fp16
+    // holds 2^15) and the row's largest term >= 2^-(spread - 7): with spread <= 15 that is >= 2^-8, so
+    // fp16 subnormal rounding (2^-25 absolute) stays below 2^-17 of the largest term.
+    const float bw_spread = bw_max - bw_min;
+    const bool bound_ok = __all_sync(0xffffffffu, bw_spread <= 15.f) && !exact_max;
+    bw_max -= fminf(bw_spread, 7.f);
     const uint32_t bh_addr = smem_u32(sBh + row);
     auto lds_h = [](uint32_t addr) -> float {
       unsigned short v;
@@ -2109,9 +2165,29 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
       const float bh0 = kLog2e * lds_h(bh_addr + (2 * j) * 256), bh1 = kLog2e * lds_h(bh_addr + (2 * j + 1) * 256);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // ---- pass 1: tile maximum (chunks 0, 1 = key row 2j; chunks 2, 3 = key row 2j + 1) ----
+      // ---- pass 1 (chunks 0, 1 = key row 2j; chunks 2, 3 = key row 2j + 1).  Softmax is shift-
+      // invariant and the running maximum only has to keep 2^(x - m) in fp16 range, so where the 64
+      // column biases of every row of this warp lie within 15 (log2 units) of each other the BOUND
+      // max(scale * s) + max(bw) + bh per key row, shifted as explained above, does and the 128
+      // FMAs of the exact maximum are skipped; other warps take the exact maximum. ----
       float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-      {
+      if (bound_ok) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_x32(tm, ra);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&r)[32] = (c & 1) ? rb : ra;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_x32(tm + 32 * (c + 1), (c & 1) ? ra : rb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float u0 = fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+            const float u1 = fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            if (c < 2) { a0 = fmaxf(a0, u0); a1 = fmaxf(a1, u1); }
+            else { a2 = fmaxf(a2, u0); a3 = fmaxf(a3, u1); }
+          }
+        }
+      } else {
         uint32_t ra[32], rb[32];
         tmem_ld_x32(tm, ra);
 #pragma unroll
@@ -2128,7 +2204,9 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
           }
         }
       }
-      const float m_tile = fmaxf(fmaxf(a0, a1) + bh0, fmaxf(a2, a3) + bh1);
+      const float m_tile = bound_ok
+          ? fmaxf(fmaf(fmaxf(a0, a1), c_scale, bh0), fmaf(fmaxf(a2, a3), c_scale, bh1)) + bw_max
+          : fmaxf(fmaxf(a0, a1) + bh0, fmaxf(a2, a3) + bh1);
       const float m_new = fmaxf(m_used, m_tile);
       if (j == 0) {
         m_used = m_new;
@@ -2255,7 +2333,7 @@ int launch_attn_glob3(const void* qkv, const void* rph, const void* rpw, void* o
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "attn_glob3"); rc != SAMQ_OK) return rc;
   dim3 grid(C::kQTiles, heads, B);
   kern<<<grid, kGlob3Threads, C::kSmemBytes, st>>>(*m_main, *m_tail, *h_main, *h_tail, *w_main, *w_tail,
-                                                  reinterpret_cast<__half*>(out), heads, scale, relw_mode);
+                                                  reinterpret_cast<__half*>(out), heads, scale, relw_mode, exact_max_requested());
   count_launch();
   return check_launch("attn_glob3_kernel");
 }

@@ -52,10 +52,12 @@ def test_windowed_item_scheduling(cuda_device, B, heads, hd):
 
 
 @pytest.mark.parametrize("env,val,B,E", [("SAMQ_ATTN_WIN", "v2", 25, 14), ("SAMQ_ATTN_WIN", "v1", 25, 14),
-                                         ("SAMQ_ATTN_GLOB", "v1", 1, 64), ("SAMQ_ATTN_GLOB", "v2", 1, 64)])
+                                         ("SAMQ_ATTN_GLOB", "v1", 1, 64), ("SAMQ_ATTN_GLOB", "v2", 1, 64),
+                                         ("SAMQ_ATTN_MAX", "exact", 25, 14), ("SAMQ_ATTN_MAX", "exact", 1, 64)])
 def test_ablation_kernels_agree_with_default(cuda_device, monkeypatch, env, val, B, E):
-    """The earlier kernel designs stay selectable (SAMQ_ATTN_WIN=v1|v2, SAMQ_ATTN_GLOB=v1) for
-    A/B timing; they must compute the same function."""
+    """The earlier kernel designs stay selectable (SAMQ_ATTN_WIN=v1|v2, SAMQ_ATTN_GLOB=v1|v2), and so
+    does the exact row maximum (SAMQ_ATTN_MAX=exact), for A/B timing; they must compute the same
+    function."""
     qkv, rph, rpw = make_inputs(B, E, 4, 80, seed=11)
     args = (qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), B, E, E, 4, 80 ** -0.5)
     new = ops.attn_relpos(*args)
@@ -102,6 +104,23 @@ def test_large_logits_exercise_the_lazy_rescale(cuda_device):
     ref = oe.attention_core(qkv, rph, rpw, 1, 64, 64, 2, 80 ** -0.5, "reference", round_tables=True)
     err, mag, cos = report(out, ref)
     assert err <= 2e-2 * max(1.0, mag) and cos >= 0.999, (err, mag, cos)
+
+
+@pytest.mark.parametrize("B,E", [(25, 14), (1, 64)])
+@pytest.mark.parametrize("rp_std,tol", [(0.0, 1.0), (0.05, 1.0), (0.3, 1.0), (1.5, 5.0)])
+def test_bound_and_exact_row_maximum_paths(cuda_device, B, E, rp_std, tol):
+    """The softmax replaces the row maximum by a bound when the column biases of a warp's rows lie
+    within 2^15 of each other and takes the exact maximum otherwise: zero tables (the reference's
+    benchmark init, image_encoder.py:235-236), narrow, default and wide bias spreads -- the last
+    one sends every warp down the exact path (q.Rw has sigma ~ 10 in log2 units)."""
+    qkv, rph, rpw = make_inputs(B, E, 2, 80, seed=5, std=0.5, rp_std=max(rp_std, 1e-9))
+    if rp_std == 0.0:
+        rph.zero_(), rpw.zero_()
+    out = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), B, E, E, 2, 80 ** -0.5)
+    ref = oe.attention_core(qkv, rph, rpw, B, E, E, 2, 80 ** -0.5, "reference", round_tables=True)
+    err, mag, cos = report(out, ref)
+    assert not torch.isnan(out).any()
+    assert err <= tol * ATOL * max(1.0, mag) and cos >= 0.9999, (err, mag, cos)
 
 
 @pytest.mark.parametrize("name,size", [("attn_win", 14), ("attn_glob", 64)])
