@@ -151,21 +151,23 @@ def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, monkeypatch, K, N
     assert err <= ULP * mag + 1e-6 and cos >= 0.99999
 
 
-def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, monkeypatch):
-    """M >= 12288 takes unpack-once + dense GEMM; it must equal the fused kernel bit for bit."""
-    K, N, M = 1280, 1280, 12288 + 77
-    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=13)
+@pytest.mark.parametrize("K,N,gs", [(1280, 1280, 128), (320, 256, 64), (64, 512, 64), (192, 256, 64)])
+def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, monkeypatch, K, N, gs):
+    """M >= 12288 takes unpack-once + dense GEMM; it must equal the fused kernel bit for bit.
+    K = 320, 64, 192: short reductions (fewer k-blocks than pipeline stages, odd counts)."""
+    M = 12288 + 77
+    qw, qz, sc, _ = rand_packed(K, N, 4, gs, seed=13)
     tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
     x = torch.randn(M, K, device=cuda_device).half()
     b = torch.randn(N, device=cuda_device).half()
     monkeypatch.delenv("SAMQ_GEMM", raising=False)
-    y_auto = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=_lib.EPI_GELU)
+    y_auto = ops.qlinear(x, tq, tz, ts, 4, gs, b, epilogue=_lib.EPI_GELU)
     monkeypatch.setenv("SAMQ_GEMM", "fused")
-    y_fused = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=_lib.EPI_GELU)
+    y_fused = ops.qlinear(x, tq, tz, ts, 4, gs, b, epilogue=_lib.EPI_GELU)
     assert torch.equal(y_auto, y_fused)
     # and the fast transposed int4 dequant kernel is bit-exact against the oracle
-    wt = ops.unpack_dequant(tq, tz, ts, 4, 128, transposed=True)
-    ref = oq.dequant(qw, qz, sc, 4, 128)
+    wt = ops.unpack_dequant(tq, tz, ts, 4, gs, transposed=True)
+    ref = oq.dequant(qw, qz, sc, 4, gs)
     assert np.array_equal(wt.t().contiguous().cpu().numpy().view(np.uint16), ref.view(np.uint16))
 
 
