@@ -86,7 +86,8 @@ class GraphedEncoder:
     visible, so the whole forward is captured once (static input/output buffers, TMA
     descriptors keyed on the stable buffer addresses) and replayed.  ``__call__`` copies the
     input into the static buffer (device-to-device, or host-to-device for pinned input) and
-    returns the static output tensor (valid until the next call).
+    returns the static output tensor (valid until the next call); ``run_host`` is the pipelined
+    host-buffer form.
     """
 
     def __init__(self, encoder, example: torch.Tensor, warmup: int = 2):
@@ -113,3 +114,47 @@ class GraphedEncoder:
         self.static_in.copy_(images, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+    def _init_pipeline(self) -> None:
+        dev = self.static_in.device
+        self._h2d, self._d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._stage_in = [torch.empty_like(self.static_in) for _ in range(2)]
+        self._stage_out = [torch.empty_like(self.static_out) for _ in range(2)]
+        self._in_ready, self._in_free, self._out_ready, self._out_free = (
+            [torch.cuda.Event() for _ in range(2)] for _ in range(4))
+        self._n = 0
+
+    @torch.no_grad()
+    def run_host(self, host_in: torch.Tensor, host_out: torch.Tensor) -> torch.cuda.Event:
+        """Serving-loop form of ``__call__`` for PINNED host buffers: asynchronous, and pipelined
+        across consecutive calls.  The host-to-device copy of call i+1 and the device-to-host copy
+        of call i-1 run on two copy streams underneath the encoder of call i (staging buffers are
+        double-buffered; a device-to-device copy moves them in and out of the graph's static
+        tensors, 0.2 ms per call at batch 32 against ~5 ms of PCIe time).  Returns the event after
+        which ``host_out`` holds this call's embeddings (``host_in`` may be overwritten by then
+        too)."""
+        if not (host_in.is_pinned() and host_out.is_pinned()):
+            raise ValueError("run_host needs pinned host tensors (torch.Tensor.pin_memory())")
+        if not hasattr(self, "_h2d"):
+            self._init_pipeline()
+        k, first = self._n & 1, self._n < 2
+        self._n += 1
+        cur = torch.cuda.current_stream(self.static_in.device)
+        with torch.cuda.stream(self._h2d):
+            if not first:
+                self._h2d.wait_event(self._in_free[k])      # the encoder two calls back has consumed it
+            self._stage_in[k].copy_(host_in, non_blocking=True)
+            self._in_ready[k].record(self._h2d)
+        cur.wait_event(self._in_ready[k])
+        self.static_in.copy_(self._stage_in[k])
+        self._in_free[k].record(cur)
+        self.graph.replay()
+        if not first:
+            cur.wait_event(self._out_free[k])               # its previous content has reached the host
+        self._stage_out[k].copy_(self.static_out)
+        self._out_ready[k].record(cur)
+        with torch.cuda.stream(self._d2h):
+            self._d2h.wait_event(self._out_ready[k])
+            host_out.copy_(self._stage_out[k], non_blocking=True)
+            self._out_free[k].record(self._d2h)
+        return self._out_free[k]

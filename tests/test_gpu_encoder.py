@@ -126,3 +126,34 @@ def test_vit_l_width_blocks_batched(cuda_device, tmp_path):
     err, mag, cos = report(y, ref)
     print(f"ViT-L width, batch 3: max-abs {err:.3e} (max|ref| {mag:.3f}) cosine {cos:.7f}")
     assert err <= 1.5e-2 * mag and cos >= 0.9999
+
+
+def test_graphed_encoder_replay_and_pipelined_host_calls(cuda_device):
+    """GraphedEncoder: the captured forward equals the eager one bit for bit, and run_host -- H2D
+    of call i+1 / D2H of call i-1 on copy streams under the encoder of call i, double-buffered
+    staging -- returns every call's own result in order, also when one output buffer per call is
+    reused after its event."""
+    from sam_quantization_b200.launcher import GraphedEncoder
+    from sam_quantization_b200.synthetic import random_quantized_encoder
+
+    enc = random_quantized_encoder("vit_b", 4, 128, seed=3, device=cuda_device, embed_dim=256, depth=2,
+                                   num_heads=4, global_attn_indexes=(1,))
+    g = torch.Generator().manual_seed(9)
+    host_in = [torch.randn(2, 3, 1024, 1024, generator=g).half().pin_memory() for _ in range(5)]
+    with torch.no_grad():
+        eager = [enc(h.to(cuda_device)).cpu() for h in host_in]
+    assert not torch.equal(eager[0], eager[1])
+    ge = GraphedEncoder(enc, host_in[0].to(cuda_device))
+    assert ge.kernels_per_replay > 0
+    assert torch.equal(ge(host_in[1].to(cuda_device)).cpu(), eager[1])
+    host_out = [torch.empty(2, 256, 64, 64, dtype=torch.float16).pin_memory() for _ in range(5)]
+    events = [ge.run_host(host_in[i], host_out[i]) for i in range(5)]     # issued back to back
+    for i, ev in enumerate(events):
+        ev.synchronize()
+        assert torch.equal(host_out[i], eager[i]), f"call {i}"
+    # a second round through the same pipeline object, reusing ONE output buffer
+    for i in (3, 0, 4):
+        ge.run_host(host_in[i], host_out[0]).synchronize()
+        assert torch.equal(host_out[0], eager[i])
+    with pytest.raises(ValueError):
+        ge.run_host(host_in[0].clone(), host_out[0])          # not pinned
