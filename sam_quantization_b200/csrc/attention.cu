@@ -1939,7 +1939,7 @@ struct G3Cfg {
   static constexpr int oV = oK1 + kTileBytes;       // rel_pos_w first
   static constexpr int oBh = oV + kTileBytes;       // __half [64][128]
   static constexpr int oBars = oBh + 64 * 128 * 2;
-  static constexpr int kNumBars = 12;
+  static constexpr int kNumBars = 15;
   static constexpr int kSmemBytes = oBars + kNumBars * 8 + 16 + 1024;
   static constexpr int cO = 128;
   static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
@@ -1969,10 +1969,11 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
   uint64_t* v_empty = bars + 6;
   uint64_t* t_full = bars + 7;
   uint64_t* t_done = bars + 8;      // count 4
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_full = bars + 10;     // count 4
-  uint64_t* o_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 9;      // [2]: S buffer of the even / odd half-tiles
+  uint64_t* p_full = bars + 11;     // [2], count 4
+  uint64_t* o_done = bars + 13;
+  uint64_t* pv_done = bars + 14;    // one completion per P.V (only the lazy rescale waits for it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -1985,7 +1986,8 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
     mbar_init(&k_empty[0], 1); mbar_init(&k_empty[1], 1);
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(t_full, 1); mbar_init(t_done, 4);
-    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1);
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full[0], 4); mbar_init(&p_full[1], 4);
+    mbar_init(o_done, 1); mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 256);
@@ -2035,53 +2037,80 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
     }
   } else if (warp == 5) {
     // ============================ MMA issuer ============================
-    constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0);
+    // A 128-key K / V tile is processed as two HALF-TILES of 64 keys (= one key row of the image)
+    // with their own S buffers (TMEM columns [0, 64) and [64, 128)): S(h+2) is formed while the
+    // softmax warps work on S(h+1), so they go from one half-tile to the next without waiting for
+    // a QK^T (with one 128-column S buffer a third of their time was that wait).
+    constexpr uint32_t idesc_tab = make_idesc_f16(128, 128, 0);
+    constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, 0);
     constexpr uint32_t idesc_pv_main = make_idesc_f16(128, 64, 1);
     constexpr uint32_t idesc_pv_tail = make_idesc_f16(128, 16, 1);
     const uint64_t q_main = make_smem_desc(smem_u32(sQ), 0, 1024, kLayoutSw128);
     const uint64_t q_tail = make_smem_desc(smem_u32(sQ + C::kMainBytes), 0, 256, kLayoutSw32);
-    auto mma_q_times = [&](uint32_t d_tmem, const uint8_t* tile, uint64_t* bar0, uint64_t* bar1) {
+    auto mma_q_times = [&](uint32_t d_tmem, const uint8_t* tile, uint32_t idesc, uint64_t* bar0, uint64_t* bar1) {
       const uint64_t b_main = make_smem_desc(smem_u32(tile), 0, 1024, kLayoutSw128);
       const uint64_t b_tail = make_smem_desc(smem_u32(tile + C::kMainBytes), 0, 256, kLayoutSw32);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc_qk, k > 0);
-        if (C::kTail) tc_mma_ss(d_tmem, q_tail, b_tail, idesc_qk, 1);
+          tc_mma_ss(d_tmem, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc, k > 0);
+        if (C::kTail) tc_mma_ss(d_tmem, q_tail, b_tail, idesc, 1);
         if (bar0) tc_commit(bar0);
         if (bar1) tc_commit(bar1);
       }
       __syncwarp();
     };
+    // S(h) = Q . K(tile h / 2, keys 64 (h & 1) ..)^T into S buffer h & 1; the K slot is released
+    // by its second half
+    auto mma_qk_half = [&](int h) {
+      const int hh = h & 1;
+      const uint8_t* tile = ((h >> 1) & 1) ? sK1 : sK0;
+      const uint64_t b_main = make_smem_desc(smem_u32(tile + hh * 8192), 0, 1024, kLayoutSw128);
+      const uint64_t b_tail = make_smem_desc(smem_u32(tile + C::kMainBytes + hh * 2048), 0, 256, kLayoutSw32);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(tmem_base + 64 * hh, q_main + (k * 32 >> 4), b_main + (k * 32 >> 4), idesc_qk, k > 0);
+        if (C::kTail) tc_mma_ss(tmem_base + 64 * hh, q_tail, b_tail, idesc_qk, 1);
+        tc_commit(&s_full[hh]);
+        if (hh) tc_commit(&k_empty[(h >> 1) & 1]);
+      }
+      __syncwarp();
+    };
     mbar_wait(q_full, 0);
     tc_fence_after();
-    mma_q_times(tmem_base + 0, sK1, nullptr, nullptr);        // T_h = Q . rel_pos_h^T
-    mma_q_times(tmem_base + 128, sV, t_full, nullptr);        // T_w = Q . rel_pos_w^T
+    mma_q_times(tmem_base + 0, sK1, idesc_tab, nullptr, nullptr);        // T_h = Q . rel_pos_h^T
+    mma_q_times(tmem_base + 128, sV, idesc_tab, t_full, nullptr);        // T_w = Q . rel_pos_w^T
     mbar_wait(t_done, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
-    mma_q_times(tmem_base, sK0, s_full, &k_empty[0]);
-    for (int j = 0; j < T; ++j) {
-      mbar_wait(p_full, j & 1);
-      mbar_wait(v_full, j & 1);
+    mma_qk_half(0);
+    mma_qk_half(1);
+    for (int h = 0; h < 2 * T; ++h) {
+      const int hh = h & 1, j = h >> 1;
+      mbar_wait(&p_full[hh], j & 1);
+      if (hh == 0) mbar_wait(v_full, j & 1);
       tc_fence_after();
       const uint64_t v_main0 = make_smem_desc(smem_u32(sV), C::kMainBytes, 1024, kLayoutSw128);
       const uint64_t v_tail0 = make_smem_desc(smem_u32(sV + C::kMainBytes), C::kTailBytes, 256, kLayoutSw32);
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          tc_mma_ts(tmem_base + C::cO, tmem_base + ks * 8, v_main0 + (ks * 2048 >> 4), idesc_pv_main, acc);
-          if (C::kTail) tc_mma_ts(tmem_base + C::cO + 64, tmem_base + ks * 8, v_tail0 + (ks * 512 >> 4), idesc_pv_tail, acc);
+        for (int kk = 0; kk < 4; ++kk) {
+          const int ks = 4 * hh + kk;                       // 16-key step inside the 128-key V tile
+          const uint32_t acc = (h > 0 || kk > 0) ? 1u : 0u;
+          tc_mma_ts(tmem_base + C::cO, tmem_base + 64 * hh + kk * 8, v_main0 + (ks * 2048 >> 4), idesc_pv_main, acc);
+          if (C::kTail) tc_mma_ts(tmem_base + C::cO + 64, tmem_base + 64 * hh + kk * 8, v_tail0 + (ks * 512 >> 4), idesc_pv_tail, acc);
         }
-        tc_commit(v_empty);
-        if (j == T - 1) tc_commit(o_done);
+        tc_commit(pv_done);
+        if (hh) tc_commit(v_empty);
+        if (h == 2 * T - 1) tc_commit(o_done);
       }
       __syncwarp();
-      if (j + 1 < T) {
-        mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+      if (h + 2 < 2 * T) {
+        // S(h+2) overwrites P(h): the tensor pipe retires in order, P.V(h) was issued above
+        if (hh == 0) mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
         tc_fence_after();
-        mma_q_times(tmem_base, ((j + 1) & 1) ? sK1 : sK0, s_full, &k_empty[(j + 1) & 1]);
+        mma_qk_half(h + 2);
       }
     }
   } else {
@@ -2161,112 +2190,92 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
 
     float m_used = -INFINITY, l = 0.f;
 #pragma unroll 1
-    for (int j = 0; j < T; ++j) {
-      const float bh0 = kLog2e * lds_h(bh_addr + (2 * j) * 256), bh1 = kLog2e * lds_h(bh_addr + (2 * j + 1) * 256);
-      mbar_wait(s_full, j & 1);
+    for (int h = 0; h < 2 * T; ++h) {
+      // half-tile h = key row h of the image: 64 scores per query row in S buffer h & 1
+      const int hh = h & 1;
+      const uint32_t ts = tm + 64 * hh;
+      const float bh0 = kLog2e * lds_h(bh_addr + h * 256);
+      mbar_wait(&s_full[hh], (h >> 1) & 1);
       tc_fence_after();
-      // ---- pass 1 (chunks 0, 1 = key row 2j; chunks 2, 3 = key row 2j + 1).  Softmax is shift-
-      // invariant and the running maximum only has to keep 2^(x - m) in fp16 range, so where the 64
-      // column biases of every row of this warp lie within 15 (log2 units) of each other the BOUND
-      // max(scale * s) + max(bw) + bh per key row, shifted as explained above, does and the 128
-      // FMAs of the exact maximum are skipped; other warps take the exact maximum. ----
-      float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+      // ---- pass 1.  Softmax is shift-invariant and the running maximum only has to keep
+      // 2^(x - m) in fp16 range, so where the 64 column biases of every row of this warp lie within
+      // 15 (log2 units) of each other the BOUND max(scale * s) + max(bw) + bh, shifted as explained
+      // above, does and the 64 FMAs of the exact maximum are skipped; other warps take the exact
+      // maximum. ----
+      float a0 = -INFINITY, a1 = -INFINITY;
+      uint32_t ra[32], rb[32];
+      tmem_ld_x32(ts, ra);
+      tmem_ld_x32(ts + 32, rb);
+      tmem_ld_wait();
       if (bound_ok) {
-        uint32_t ra[32], rb[32];
-        tmem_ld_x32(tm, ra);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&r)[32] = (c & 1) ? rb : ra;
-          tmem_ld_wait();
-          if (c < 3) tmem_ld_x32(tm + 32 * (c + 1), (c & 1) ? ra : rb);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t (&r)[32] = c ? rb : ra;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float u0 = fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-            const float u1 = fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            if (c < 2) { a0 = fmaxf(a0, u0); a1 = fmaxf(a1, u1); }
-            else { a2 = fmaxf(a2, u0); a3 = fmaxf(a3, u1); }
+            a0 = fmaxf(a0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+            a1 = fmaxf(a1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
           }
         }
       } else {
-        uint32_t ra[32], rb[32];
-        tmem_ld_x32(tm, ra);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&r)[32] = (c & 1) ? rb : ra;
-          tmem_ld_wait();
-          if (c < 3) tmem_ld_x32(tm + 32 * (c + 1), (c & 1) ? ra : rb);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t (&r)[32] = c ? rb : ra;
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(r[i]), c_scale, bw[(c & 1) * 32 + i]);
-            const float x1 = fmaf(__uint_as_float(r[i + 1]), c_scale, bw[(c & 1) * 32 + i + 1]);
-            if (c < 2) { a0 = fmaxf(a0, x0); a1 = fmaxf(a1, x1); }
-            else { a2 = fmaxf(a2, x0); a3 = fmaxf(a3, x1); }
+            a0 = fmaxf(a0, fmaf(__uint_as_float(r[i]), c_scale, bw[c * 32 + i]));
+            a1 = fmaxf(a1, fmaf(__uint_as_float(r[i + 1]), c_scale, bw[c * 32 + i + 1]));
           }
         }
       }
-      const float m_tile = bound_ok
-          ? fmaxf(fmaf(fmaxf(a0, a1), c_scale, bh0), fmaf(fmaxf(a2, a3), c_scale, bh1)) + bw_max
-          : fmaxf(fmaxf(a0, a1) + bh0, fmaxf(a2, a3) + bh1);
+      const float m_tile = bound_ok ? fmaf(fmaxf(a0, a1), c_scale, bh0) + bw_max : fmaxf(a0, a1) + bh0;
       const float m_new = fmaxf(m_used, m_tile);
-      if (j == 0) {
+      if (h == 0) {
         m_used = m_new;
       } else if (__any_sync(0xffffffffu, m_new > m_used + 8.f)) {
-        // lazy rescale.  P.V(j-1) was issued before QK^T(j) and the tensor pipe retires in order, so
-        // s_full(j) already implies that O is complete up to tile j-1.
+        // lazy rescale.  P.V(h-1) was issued when this warpgroup finished half-tile h-1 and may
+        // still be accumulating into O: wait for its completion first.
+        mbar_wait(pv_done, (h - 1) & 1);
+        tc_fence_after();
         const float alpha = ex2(m_used - m_new);
         l *= alpha;
         m_used = m_new;
         const uint32_t o_tmem = tm + C::cO;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(o_tmem + c * 32, r);
+        // rare path: 8 columns at a time, so that it does not take registers from the common one
+#pragma unroll 1
+        for (int c = 0; c < HD / 8; ++c) {
+          uint32_t r[8];
+          tmem_ld_x8(o_tmem + c * 8, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_x32(o_tmem + c * 32, r);
-        }
-        if (C::kTail) {
-          uint32_t r[16];
-          tmem_ld_x16(o_tmem + 64, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_x16(o_tmem + 64, r);
+          for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x8(o_tmem + c * 8, r);
         }
         tmem_st_wait();
       }
-      // ---- pass 2: P = 2^(x - m) as fp16 pairs over the S columns, behind the read pointer ----
-      const float mm0 = m_used - bh0, mm1 = m_used - bh1;
+      // ---- pass 2: P = 2^(x - m) as fp16 pairs over the half-tile's own S columns (the scores
+      // are still in registers from pass 1) ----
+      const float mm = m_used - bh0;
       float s0 = 0.f, s1 = 0.f;
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld_x32(tm, ra);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&r)[32] = (c & 1) ? rb : ra;
-          tmem_ld_wait();
-          if (c < 3) tmem_ld_x32(tm + 32 * (c + 1), (c & 1) ? ra : rb);
-          const float mm = c < 2 ? mm0 : mm1;
-          uint32_t pk[16];
+      for (int c = 0; c < 2; ++c) {
+        uint32_t (&r)[32] = c ? rb : ra;
+        uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[i]), c_scale, bw[(c & 1) * 32 + i]) - mm);
-            const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), c_scale, bw[(c & 1) * 32 + i + 1]) - mm);
-            s0 += p0;
-            s1 += p1;
-            pk[i >> 1] = pack_h2(p0, p1);
-          }
-          // chunk c's P goes to columns [16c, 16c+16): behind chunk c's and the prefetched chunk
-          // c+1's S columns ([32c, 32c+64))
-          tmem_st_x16(tm + 16 * c, pk);
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[i]), c_scale, bw[c * 32 + i]) - mm);
+          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), c_scale, bw[c * 32 + i + 1]) - mm);
+          s0 += p0;
+          s1 += p1;
+          pk[i >> 1] = pack_h2(p0, p1);
         }
+        tmem_st_x16(ts + 16 * c, pk);
       }
       l += s0 + s1;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[hh]);
     }
 
     // ---- epilogue: O / l ----
