@@ -188,6 +188,12 @@ int samq_unpartition_residual(const void* windows, const void* shortcut, void* o
  * bias and the positional embedding as the residual. */
 int samq_patchify_fwd(const void* x, void* out, int B, int C, int H, int W, int P, void* stream);
 
+/* The neck's 3x3 convolution (segment_anything image_encoder.py:96-103: Conv2d(256, 256, 3,
+ * padding=1, bias=False)) as a GEMM: x fp16 NHWC [B,H,W,C] -> out fp16 [B*H*W, 9*C] with
+ * out[(b,h,w), (ky*3+kx)*C + c] = x[b, h+ky-1, w+kx-1, c] (zero outside the image); feed it to
+ * samq_dense_linear_fwd with the weight laid out [O, (ky, kx, c)].  The result is NHWC. */
+int samq_im2col3x3_fwd(const void* x, void* out, int B, int H, int W, int C, void* stream);
+
 /* out = a + b over n fp16 elements (image_encoder.py:204; global-attention blocks). */
 int samq_add(const void* a, const void* b, void* out, int64_t n, void* stream);
 

@@ -76,6 +76,7 @@ SIGNATURES = {
         c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "samq_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "samq_patchify_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "samq_im2col3x3_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

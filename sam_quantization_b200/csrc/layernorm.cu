@@ -403,6 +403,49 @@ extern "C" int samq_patchify_fwd(const void* x, void* out, int B, int C, int H, 
   return check_launch("patchify_kernel");
 }
 
+namespace samq {
+namespace {
+// 3x3 / stride 1 / zero-padding 1 neighbourhoods of an NHWC tensor as GEMM rows (the neck's second
+// convolution, image_encoder.py:96-103, is  rows x [9 C] . W[O, (ky, kx, c)]^T):
+// out[(b, h, w), (ky*3 + kx) * C + c] = x[b, h + ky - 1, w + kx - 1, c], zero outside the image.
+// One thread per 16-byte chunk; a warp writes 512 contiguous bytes and reads 512 contiguous bytes.
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ out, int B, int H, int W, int C) {
+  const int cpt = C / 8;                       // 16-byte chunks per tap
+  const int64_t total = static_cast<int64_t>(B) * H * W * 9 * cpt;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % cpt);
+  int64_t t = idx / cpt;
+  const int tap = static_cast<int>(t % 9);
+  t /= 9;                                      // output pixel (b, h, w)
+  const int w = static_cast<int>(t % W);
+  const int h = static_cast<int>((t / W) % H);
+  const int b = static_cast<int>(t / (static_cast<int64_t>(W) * H));
+  const int hs = h + tap / 3 - 1, ws = w + tap % 3 - 1;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (hs >= 0 && hs < H && ws >= 0 && ws < W)
+    v = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(b) * H + hs) * W + ws) * C + chunk * 8);
+  *reinterpret_cast<uint4*>(out + t * (9 * static_cast<int64_t>(C)) + tap * C + chunk * 8) = v;
+}
+}  // namespace
+}  // namespace samq
+
+extern "C" int samq_im2col3x3_fwd(const void* x, void* out, int B, int H, int W, int C, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(x && out, SAMQ_ERR_BAD_ARG, "samq_im2col3x3_fwd: null pointer");
+  SAMQ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, SAMQ_ERR_BAD_SHAPE,
+               "samq_im2col3x3_fwd: B=%d H=%d W=%d C=%d (C %% 8 == 0)", B, H, W, C);
+  SAMQ_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16 == 0, SAMQ_ERR_BAD_ARG,
+               "samq_im2col3x3_fwd: pointers must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * H * W * 9 * (C / 8);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  im2col3x3_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), B, H, W, C);
+  count_launch();
+  return check_launch("im2col3x3_kernel");
+}
+
 extern "C" int samq_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
   using namespace samq;
   SAMQ_REQUIRE(a && b && out, SAMQ_ERR_BAD_ARG, "samq_add: null pointer");

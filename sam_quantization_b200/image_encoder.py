@@ -21,7 +21,8 @@ fused B200 path:
     That eager path is NOT a fallback of the quantized path: a quantized block on a
     non-CUDA tensor raises.
 
-Patch embedding and neck (0.26 % of FLOPs) stay on cuDNN/ATen.
+Patch embedding and neck (0.26 % of FLOPs) run on the same kernels: patch / 3x3
+re-layouts + the dense tcgen05 GEMM, LayerNorm2d on the token LayerNorm kernel.
 """
 from __future__ import annotations
 
@@ -279,6 +280,7 @@ class ImageEncoderViT(nn.Module):
                 window_size=window_size if i not in global_attn_indexes else 0,
                 input_size=(img_size // patch_size, img_size // patch_size)))
         self._pos_cache = {}
+        self._conv3_cache = {}
         self.neck = nn.Sequential(
             nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False),
             LayerNorm2d(out_chans),
@@ -320,16 +322,28 @@ class ImageEncoderViT(nn.Module):
 
     def _neck_fused(self, x: torch.Tensor) -> torch.Tensor:
         """conv1x1 as a tcgen05 GEMM, LayerNorm2d as the token LayerNorm kernel (channels are
-        the last dim in NHWC), conv3x3 on cuDNN in channels_last (no layout copies)."""
+        the last dim in NHWC), conv3x3 as 3x3-neighbourhood rows (``samq_im2col3x3_fwd``) times
+        the weight laid out ``[O, (ky, kx, c)]`` on the same GEMM -- everything stays NHWC."""
         c1, n1, c3, n2 = self.neck[0], self.neck[1], self.neck[2], self.neck[3]
         B, H, W, D = x.shape
         y = ops.dense_linear(x.view(-1, D), c1.weight.view(c1.out_channels, D))
         y = ops.layernorm(y, n1.weight, n1.bias, n1.eps)
-        y = y.view(B, H, W, -1).permute(0, 3, 1, 2)                     # NCHW view, channels_last memory
-        y = F.conv2d(y, c3.weight.contiguous(memory_format=torch.channels_last), None, padding=c3.padding)
-        y = y.permute(0, 2, 3, 1).contiguous()                          # NHWC
+        C = y.shape[-1]
+        if (c3.kernel_size == (3, 3) and c3.stride == (1, 1) and c3.padding == (1, 1) and c3.bias is None
+                and c3.groups == 1 and C % 8 == 0 and (9 * C) % 64 == 0 and c3.out_channels % 256 == 0
+                and os.environ.get("SAMQ_NECK_CONV", "") != "cudnn"):
+            key = (c3.weight.data_ptr(), c3.weight._version, str(c3.weight.device))
+            w3 = self._conv3_cache.get(key)
+            if w3 is None:      # [O, C, 3, 3] -> [O, (ky, kx, c)], once per weight version
+                w3 = c3.weight.detach().permute(0, 2, 3, 1).reshape(c3.out_channels, 9 * C).contiguous()
+                self._conv3_cache = {key: w3}
+            y = ops.dense_linear(ops.im2col3x3(y.view(B, H, W, C)), w3)           # [B*H*W, O], NHWC
+        else:                   # other conv shapes / the ablation switch: cuDNN in channels_last
+            y = y.view(B, H, W, -1).permute(0, 3, 1, 2)
+            y = F.conv2d(y, c3.weight.contiguous(memory_format=torch.channels_last), None, padding=c3.padding)
+            y = y.permute(0, 2, 3, 1).contiguous().view(B * H * W, -1)
         y = ops.layernorm(y, n2.weight, n2.bias, n2.eps)
-        return y.permute(0, 3, 1, 2).contiguous()                       # NCHW like the reference
+        return y.view(B, H, W, -1).permute(0, 3, 1, 2).contiguous()     # NCHW like the reference
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self._fused_stem_ready(x):

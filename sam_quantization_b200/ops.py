@@ -227,6 +227,21 @@ def patchify(x: torch.Tensor, patch: int) -> torch.Tensor:
     return out
 
 
+def im2col3x3(x: torch.Tensor) -> torch.Tensor:
+    """NHWC ``[B, H, W, C]`` fp16 -> ``[B*H*W, 9*C]`` rows of zero-padded 3x3 neighbourhoods,
+    column order (ky, kx, c)."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x")
+    if x.dim() != 4:
+        raise ValueError("im2col3x3 expects a [B, H, W, C] tensor")
+    B, H, W, C = x.shape
+    with _dev_ctx(x):
+        out = torch.empty((B * H * W, 9 * C), dtype=torch.float16, device=x.device)
+        _lib.check(_lib.load().samq_im2col3x3_fwd(_lib.ptr(x), _lib.ptr(out), B, H, W, C,
+                                                  _lib.stream_ptr(x.device)))
+    return out
+
+
 def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _lib.require_cuda(a, "a")
     _check_half(a, "a"); _check_half(b, "b")

@@ -76,3 +76,29 @@ def test_patchify_and_fused_patch_embed(cuda_device):
     conv = torch.nn.functional.conv2d(x.float(), w.float(), b.float(), stride=16).permute(0, 2, 3, 1) + pos.float()
     err, mag, cos = report(y.view(2, 4, 6, 128), conv)
     assert err <= 2.0 ** -9 * mag and cos > 0.99999
+
+
+@pytest.mark.parametrize("B,H,W,C,O", [(2, 64, 64, 256, 256), (1, 5, 7, 64, 256), (3, 1, 1, 8, 256)])
+def test_im2col3x3_and_neck_conv(cuda_device, B, H, W, C, O):
+    """samq_im2col3x3_fwd + dense GEMM == Conv2d(C, O, 3, padding=1, bias=False) in NHWC
+    (the neck's second convolution, image_encoder.py:96-103); the re-layout is exact against
+    torch's unfold, the product is checked against an fp32 convolution on the CPU."""
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, H, W, C, generator=g).half()
+    rows = ops.im2col3x3(x.to(cuda_device))
+    assert rows.shape == (B * H * W, 9 * C)
+    unf = torch.nn.functional.unfold(x.float().permute(0, 3, 1, 2), kernel_size=3, padding=1)   # [B, C*9, H*W], (c, ky, kx)
+    ref = unf.view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C).half()          # -> (ky, kx, c)
+    assert torch.equal(rows.cpu(), ref)
+    if (9 * C) % 64 == 0:
+        w = (torch.randn(O, C, 3, 3, generator=g) * 0.05).half()
+        w3 = w.permute(0, 2, 3, 1).reshape(O, 9 * C).contiguous()
+        y = ops.dense_linear(rows, w3.to(cuda_device)).view(B, H, W, O)
+        conv = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1)
+        err, mag, cos = report(y, conv)
+        assert err <= 2.0 ** -9 * max(mag, 1.0) and cos > 0.99999
+    if H > 1 and W > 1:
+        with pytest.raises(AssertionError):                     # non-contiguous input
+            ops.im2col3x3(x.to(cuda_device).transpose(1, 2))
+    with pytest.raises(ValueError):
+        ops.im2col3x3(x.to(cuda_device).view(B * H, W, C))      # not [B, H, W, C]
