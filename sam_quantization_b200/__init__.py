@@ -17,11 +17,13 @@ import torch
 from . import _lib, ops  # noqa: F401
 from .fused_attention import QuantAttention, make_quant_attn
 from .fused_mlp import QuantMLP, make_fused_mlp
+from .gptq import GPTQ, Quantizer, encoder_pack, encoder_sequential
 from .quant_linear import QuantLinear, make_quant, matmul4, triton_matmul4
 
 __all__ = [
     "QuantLinear", "make_quant", "matmul4", "triton_matmul4", "QuantAttention", "make_quant_attn",
     "QuantMLP", "make_fused_mlp", "load_quant", "save_quant", "autotune_warmup", "ops",
+    "GPTQ", "Quantizer", "encoder_sequential", "encoder_pack",
 ]
 
 
