@@ -157,3 +157,33 @@ def test_graphed_encoder_replay_and_pipelined_host_calls(cuda_device):
         assert torch.equal(host_out[0], eager[i])
     with pytest.raises(ValueError):
         ge.run_host(host_in[0].clone(), host_out[0])          # not pinned
+
+
+def test_gptq_calibrated_encoder_on_the_cuda_path(cuda_device, tmp_path):
+    """The whole offline + online chain inside this package: fp32 encoder -> encoder_sequential
+    (GPTQ calibration on one synthetic image, CPU) -> encoder_pack -> save_quant -> load_quant on
+    the GPU -> fused CUDA forward, against the fp32 forward of the ROUNDED encoder on the CPU."""
+    import copy
+
+    from sam_quantization_b200 import gptq as G
+
+    torch.manual_seed(0)
+    kw = dict(img_size=1024, patch_size=16, use_rel_pos=True, window_size=14, embed_dim=128, depth=2,
+              num_heads=2, global_attn_indexes=(1,))
+    enc = ie.ImageEncoderViT(**kw).float().eval()
+    img = torch.from_numpy(synth.image(1, 1024, seed=2))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    qs = G.encoder_sequential(enc, [img.float()], wbits=4, nsamples=1, groupsize=64)
+    rounded = copy.deepcopy(enc)
+    with torch.no_grad():
+        ref = rounded(img.half().float())
+    G.encoder_pack(enc, qs, 4, 64)
+    sq.save_quant(enc, str(tmp_path), 4, 64)
+    enc2 = sq.load_quant(ie.ImageEncoderViT(**kw).half(), str(tmp_path), warmup_autotune=False,
+                         device=cuda_device).eval()
+    assert all(b._fused_ready() for b in enc2.blocks)
+    with torch.no_grad():
+        y = enc2(img.half().to(cuda_device))
+    assert y.shape == ref.shape == (1, 256, 64, 64)
+    err, mag, cos = report(y, ref)
+    assert err <= 6e-2 * max(1.0, mag) and cos >= 0.999, (err, mag, cos)
