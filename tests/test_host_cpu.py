@@ -147,6 +147,38 @@ def test_checkpoint_round_trip_reference_layout(tmp_path):
         sq.load_quant(Wrapper().half(), str(tmp_path), warmup_autotune=True, device=None, sub_module="image_encoder")
 
 
+def test_checkpoint_safetensors_with_act_order_groups(tmp_path):
+    """The safetensors form of the checkpoint directory (gptq_triton/__init__.py:33-44 loads it
+    strictly) including the ``g_idx`` extension for act-order groups, and the reference's
+    preference order: ``model.safetensors`` wins over a ``model.pt`` lying next to it."""
+    cfg = dict(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,))
+    p = synth.fp_state(seed=4, **cfg)
+    p["blocks.1.mlp.lin2.bias"][:] = 0
+    packed = synth.to_torch(synth.quantize_state(p, 4, 64, act_order_seed=9))
+    assert any(k.endswith(".g_idx") for k in packed)
+    enc = tiny_encoder()
+    sq.make_quant(enc, 4, 64)
+    enc.half()
+    sq._register_g_idx(enc, packed)
+    enc.load_state_dict(packed, strict=True)
+    sq.save_quant(enc, str(tmp_path), 4, 64, safetensors=True)
+    assert (tmp_path / "model.safetensors").exists() and not (tmp_path / "model.pt").exists()
+    torch.save({"garbage": torch.zeros(1)}, tmp_path / "model.pt")          # must be ignored
+    out = sq.load_quant(tiny_encoder().half(), str(tmp_path), warmup_autotune=False, device=None)
+    qkv = out.blocks[0].attn.qkv_proj
+    assert qkv.g_idx is not None and qkv.g_idx.dtype == torch.int32
+    assert torch.equal(qkv.g_idx, packed["blocks.0.attn.qkv.g_idx"].to(torch.int32))
+    assert torch.equal(qkv.qweight, packed["blocks.0.attn.qkv.qweight"])
+    assert out.blocks[1].mlp.lin2.bias is None and out.blocks[1].mlp.lin1.bias is not None
+    # strict: a missing tensor in the safetensors file is an error (the .pt form is lenient)
+    from safetensors.torch import load_file, save_file
+    st = load_file(str(tmp_path / "model.safetensors"))
+    st.pop("blocks.0.attn.qkv.scales")
+    save_file(st, str(tmp_path / "model.safetensors"))
+    with pytest.raises(RuntimeError):
+        sq.load_quant(tiny_encoder().half(), str(tmp_path), warmup_autotune=False, device=None)
+
+
 def test_eager_encoder_equals_oracle_fp32():
     """The pre-quantization host module (generic partition, both rel_w modes) vs the oracle."""
     cfg = dict(embed_dim=128, depth=2, num_heads=2, global_attn_indexes=(1,))
