@@ -48,6 +48,14 @@ def test_abi_version_and_error_strings():
     assert rc == _lib.SAMQ_ERR_BAD_SHAPE
     rc = lib.samq_layernorm_fwd(None, None, None, None, 4, 64, 1e-6, None)
     assert rc == _lib.SAMQ_ERR_BAD_ARG
+    # the re-layout entry points of the stem / neck
+    assert lib.samq_im2col3x3_fwd(None, None, 1, 4, 4, 8, None) == _lib.SAMQ_ERR_BAD_ARG
+    assert lib.samq_im2col3x3_fwd(16, 16, 1, 4, 4, 12, None) == _lib.SAMQ_ERR_BAD_SHAPE and "C=12" in _lib.last_error()
+    assert lib.samq_im2col3x3_fwd(16, 24, 1, 4, 4, 8, None) == _lib.SAMQ_ERR_BAD_ARG          # 16-byte alignment
+    assert lib.samq_patchify_fwd(16, 16, 1, 3, 60, 64, 16, None) == _lib.SAMQ_ERR_BAD_SHAPE    # H not a multiple of P
+    # the window size of the fused partition / unpartition attention is fixed
+    rc = lib.samq_attn_relpos_unpartition_fwd(16, 16, 16, 16, 1, 64, 64, 7, 16, 80, 0.1, 0, None)
+    assert rc != _lib.SAMQ_OK and "14" in _lib.last_error()
 
 
 def test_status_maps_to_reference_exception_types():
