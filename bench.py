@@ -26,10 +26,28 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-# algorithmic GFLOP per 1024x1024 image (2MKN per GEMM, windowed blocks on
-# 4900 padded tokens as the reference executes them; 4 S^2 hd per head for attention)
-GFLOP_PER_IMAGE = {"vit_b": 972.1, "vit_l": 2985.7, "vit_h": 5961.1}
-LINEAR_GFLOP_PER_IMAGE = {"vit_b": 726.1, "vit_l": 2608.8, "vit_h": 5449.0}
+# BASELINE.md section 3 quotes the REFERENCE's work per 1024x1024 image (windowed qkv / proj on the
+# 4900 zero-padded tokens it multiplies): ViT-B 972.1 / ViT-L 2985.7 / ViT-H 5961.1 GFLOP.  This
+# build does not multiply the padding rows, so `model_tflops` counts only what is
+# EXECUTED: every linear on the 4096 real tokens (2 M K N), attention 4 S^2 hd per head on the 25
+# padded windows (S = 196: the pad tokens stay real keys and their query rows are computed) and
+# on the 4096-token global blocks, the in-kernel rel-pos products 4 S (2 E) hd, patch embed + neck.
+MODEL_NAMES = ("vit_b", "vit_h", "vit_l")
+
+
+def executed_gflop_per_image(name: str) -> float:
+    from sam_quantization_b200.image_encoder import ENCODER_CONFIGS
+
+    c = ENCODER_CONFIGS[name]
+    D, depth, heads = c["embed_dim"], c["depth"], c["num_heads"]
+    hd, n_glob = D // heads, len(c["global_attn_indexes"])
+    n_win = depth - n_glob
+    tok = 4096
+    linear = depth * 2.0 * tok * (D * 3 * D + D * D + 2 * D * 4 * D)
+    attn_win = n_win * 25 * heads * (4.0 * 196 * 196 * hd + 4.0 * 196 * 28 * hd)
+    attn_glob = n_glob * heads * (4.0 * 4096 * 4096 * hd + 4.0 * 4096 * 128 * hd)
+    stem_neck = 2.0 * tok * (768 * D + D * 256 + 9 * 256 * 256)
+    return (linear + attn_win + attn_glob + stem_neck) / 1e9
 
 
 def load_peaks():
@@ -155,7 +173,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--model", default="vit_h", choices=sorted(GFLOP_PER_IMAGE))
+    ap.add_argument("--model", default="vit_h", choices=sorted(MODEL_NAMES))
     ap.add_argument("--batch", type=int, default=32,
                     help="images per GPU per step (BASELINE config 3 is a batch sweep: 8 / 16 / 32 / 64 per GPU give "
                          "179 / 182 / 185 / 188 images/s on one B200)")
@@ -402,7 +420,8 @@ def main():
                 "per_shape_MKN_us_tflops": [[list(k), round(v[1] / v[0] * 1e3, 1), round(v[2] / v[1] / 1e9, 1)]
                                             for k, v in sorted(per_shape.items())],
             },
-            "model_tflops": value * GFLOP_PER_IMAGE[args.model] / 1e3,
+            "model_tflops": value * executed_gflop_per_image(args.model) / 1e3,
+            "model_gflop_per_image_executed": executed_gflop_per_image(args.model),
         }
         if not args.no_cpu_baseline:
             try:

@@ -68,12 +68,25 @@ int samq_device_check(void);
  * bench.py reads it around the timed region for "gpu_launches". */
 uint64_t samq_launch_count(void);
 
+/* The library's developer switches (SAMQ_GEMM, SAMQ_DENSE, SAMQ_ATTN_MAX, SAMQ_PDL, and in
+ * ablation builds SAMQ_ATTN_WIN / SAMQ_ATTN_GLOB) are read from the environment ONCE, at first
+ * use -- not per call.  samq_config_reload() re-reads them (tests, A/B timing scripts).  The
+ * reference's counterpart is its per-module autotune cache (quant_linear.py:122-229). */
+void samq_config_reload(void);
+
+/* 1 iff this build contains the earlier kernel generations (`make ABLATIONS=1`); the shipped
+ * library returns 0. */
+int samq_has_ablations(void);
+
 /* Packed-weight unpack + dequantise ------------------------------------------
  * Replaces the in-kernel unpack of matmul4_kernel (quant_linear.py:291-301,
  * 312-313, 334-339) as a standalone pass:
  *   q[k,n] = field k%(32/bits) of qweight[k/(32/bits), n]      (2/4/8 bit)
  *   z[g,n] = field n%(32/bits) of qzeros[g, n/(32/bits)]
- *   W[k,n] = fp16( fp16(q*s[g,n]) - fp16((z+1)*s[g,n]) ),  g = g_idx[k] or k/groupsize
+ *   W[k,n] = fp16( q*s[g,n] - fp16((z+1)*s[g,n]) ),  g = g_idx[k] or k/groupsize
+ *            (ONE fused multiply-add after the separately rounded zero term: the rounding of the
+ *            reference's Triton kernel on this GPU -- fma.rn.f16x2 -- pinned by the
+ *            identity-matrix extraction, tests/golden/dequant_triton_b4.npz)
  * 3-bit uses the 32-values-in-3-words layout of quant.py:160-180.
  *   qweight int32 [K*bits/32, N], qzeros int32 [G, N*bits/32], scales fp16 [G, N],
  *   g_idx int32 [K] or NULL.

@@ -19,15 +19,21 @@ Plain numpy restatement of the reference algorithm (no torch, no CUDA):
   (/root/reference/gptq_triton/quant_linear.py:291-301, 312, 338).
 * ``dequant``   -- ``b * scales - (zeros + 1) * scales``
   (/root/reference/gptq_triton/quant_linear.py:313, 334-339) in three rounding forms;
-  ``stepwise`` (fp16 rounding after every op, what PyTorch gives for the literal
-  expression) is THE definition the CUDA kernels are held to bit-for-bit.
+  ``fma`` -- ``fp16(q*s - fp16((z+1)*s))``, one fused multiply-add after the separately
+  rounded zero term -- is THE definition the CUDA kernels are held to bit-for-bit: it is
+  what the reference's Triton kernel computes on the B200 (Triton 3.6 contracts the
+  multiply-subtract into ``fma.rn.f16x2``; 0 mismatches in 18 M elements of the
+  identity-matrix extraction ``triton_matmul4(gs, I_K, ...)`` run by ``oracle/ref_gpu.py``,
+  against 33 % for ``stepwise`` -- ``profiles/r02_ref_gpu.json``).  ``stepwise`` is what
+  PyTorch eager gives for the literal expression; ``single`` rounds ``(q-z-1)*s`` once.
 * ``qlinear``   -- ``x @ W + bias`` with fp32 accumulation
   (/root/reference/gptq_triton/quant_linear.py:341, 431-435).
 
 Parity pin: ``tests/golden/make_golden.py`` runs the reference's own
-``pack_linear`` (AST-extracted), ``Quantizer`` and the literal torch dequant
-expression in this container and stores their outputs; ``tests/test_oracle_quant.py``
-checks this module against those fixtures bit-for-bit.  bits 2/3/8 in QuantLinear and
+``pack_linear`` (AST-extracted) and ``Quantizer`` in this container and stores their
+outputs; ``tests/golden/dequant_triton_b4.npz`` holds the output of the reference's own
+Triton kernel on a B200 (written by ``oracle/ref_gpu.py --sections dequant``);
+``tests/test_oracle_quant.py`` checks this module against those fixtures bit-for-bit.  bits 2/3/8 in QuantLinear and
 ``g_idx`` are extensions: "parity unpinned by the reference" (it has no such path).
 """
 from __future__ import annotations
@@ -229,11 +235,11 @@ def unpack_qzeros(qzeros: np.ndarray, bits: int, n: int) -> np.ndarray:
 # ---------------------------------------------------------------------------
 # dequant (quant_linear.py:313, 334-339)
 # ---------------------------------------------------------------------------
-def dequant(qweight, qzeros, scales, bits: int, groupsize: int, g_idx=None, form: str = "stepwise"):
+def dequant(qweight, qzeros, scales, bits: int, groupsize: int, g_idx=None, form: str = "fma"):
     """Dequantised weight ``W[K, N]`` as fp16.
 
-    form = "stepwise": fp16(fp16(q*s) - fp16((z+1)*s))   <- the pinned definition
-           "fma"     : fp16(q*s - fp16((z+1)*s))         (if a compiler contracts)
+    form = "fma"     : fp16(q*s - fp16((z+1)*s))         <- the pinned definition (= the Triton kernel)
+           "stepwise": fp16(fp16(q*s) - fp16((z+1)*s))   (PyTorch eager on the literal expression)
            "single"  : fp16((q - (z+1)) * s)
     """
     qweight = np.asarray(qweight)
@@ -268,7 +274,7 @@ def gelu_erf(x: np.ndarray) -> np.ndarray:
 
 def qlinear(x, qweight, qzeros, scales, bits, groupsize, bias=None, g_idx=None,
             epilogue: str = "none", residual=None) -> np.ndarray:
-    """fp32-accumulated ``x @ W + bias`` on the stepwise-dequantised fp16 weight
+    """fp32-accumulated ``x @ W + bias`` on the dequantised fp16 weight (pinned "fma" form)
     (quant_linear.py:341, 431-435); returns float32 (un-rounded) so tests can state
     their tolerance against the exact value."""
     w = dequant(qweight, qzeros, scales, bits, groupsize, g_idx).astype(np.float32)

@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsamq.so")
+#: SAMQ_LIB points at another build of the library (e.g. lib/libsamq_ablations.so from `make ABLATIONS=1`)
+LIB_PATH = os.environ.get("SAMQ_LIB") or os.path.join(_HERE, "lib", "libsamq.so")
 
 SAMQ_OK = 0
 SAMQ_ERR_BAD_SHAPE = -1
@@ -35,6 +36,8 @@ SIGNATURES = {
     "samq_last_error": (c_char_p, []),
     "samq_device_check": (c_int, []),
     "samq_launch_count": (c_uint64, []),
+    "samq_config_reload": (None, []),
+    "samq_has_ablations": (c_int, []),
     "samq_unpack_dequant": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -103,6 +106,33 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+#: host-side developer switches, resolved once at import / by reload_config() -- never per call
+#:   SAMQ_GEMM=fused|dense   force one int4 QuantLinear path (the library reads the same variable)
+#:   SAMQ_PAD_SKIP=0         windowed blocks partition first and multiply the zero-padding rows
+#:   SAMQ_NECK_CONV=cudnn    neck conv3x3 through cuDNN instead of im2col + tcgen05 GEMM
+OPTIONS = {}
+
+
+def _read_options() -> None:
+    OPTIONS["gemm"] = os.environ.get("SAMQ_GEMM", "")
+    OPTIONS["pad_skip"] = os.environ.get("SAMQ_PAD_SKIP", "1") != "0"
+    OPTIONS["neck_cudnn"] = os.environ.get("SAMQ_NECK_CONV", "") == "cudnn"
+
+
+_read_options()
+
+
+def reload_config() -> None:
+    """Re-read the SAMQ_* developer switches (host side and library side).  Tests / A-B scripts
+    call this after changing the environment; the product never does."""
+    _read_options()
+    load().samq_config_reload()
+
+
+def has_ablations() -> bool:
+    return bool(load().samq_has_ablations())
 
 
 def last_error() -> str:

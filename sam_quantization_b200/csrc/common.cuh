@@ -27,6 +27,23 @@ int check_launch(const char* what);  // cudaGetLastError -> status
     }                                            \
   } while (0)
 
+// Developer switches (SAMQ_* environment variables), resolved ONCE when the library is first used
+// -- never per call -- and re-read only by samq_config_reload() (tests, A/B timing):
+//   SAMQ_GEMM      = fused | dense   force one int4 QuantLinear path (default: by M, csrc/qlinear.cu)
+//                    (2cta: the cta_group::2 fused variant, ABLATIONS builds only)
+//   SAMQ_DENSE     = 1cta            dense GEMM on the single-CTA 128x192 kernel
+//   SAMQ_ATTN_MAX  = exact           softmax warps take the exact row maximum instead of the bound
+//   SAMQ_ATTN_WIN / SAMQ_ATTN_GLOB = v1 | v2   earlier kernel designs (ABLATIONS builds only)
+//   SAMQ_PDL       = bit mask of kernel classes launched programmatically (default 3)
+struct Config {
+  int gemm;            // 0 by M, 1 fused, 2 dense, 3 2cta
+  int dense_1cta;
+  int attn_exact_max;
+  int attn_win, attn_glob;   // 0 product kernel, 1 / 2 earlier generation
+  int pdl_mask;
+};
+const Config& config();
+
 // 2-D tiled tensor map (row-major [rows, cols] of `elem_bytes` elements, box =
 // [box_rows, box_cols]); cached by content.  swizzle: 0 none, 1 32B, 2 64B, 3 128B.
 const CUtensorMap* get_tensor_map_2d(const void* base, uint64_t rows, uint64_t cols,

@@ -21,9 +21,10 @@
 //   warp 12     TMA producer: packed-weight tiles + x tiles (+ Wt tiles in dense mode)
 //   warp 13     TMEM allocator; one thread issues tcgen05.mma kind::f16 and commits -> mbarriers
 //
-// Dequant arithmetic is bit-identical to dequant.cu / oracle "stepwise" form:
-//   p = fma(1024+q, s, -1024 s)  == fp16(q*s)  (single rounding of the exact product)
-//   w = p - fp16((z+1)*s)                      (fp16 rounding)
+// Dequant arithmetic is bit-identical to dequant.cu / oracle "fma" form, which is what the
+// reference's Triton kernel computes on this GPU (tests/golden/dequant_triton_b4.npz):
+//   q  = (1024 + q) - 1024                     (exact)
+//   w  = fma(q, s, -fp16((z+1)*s))             (one fp16 rounding)
 #include "qlinear_common.cuh"
 
 #include <cstdlib>
@@ -302,8 +303,7 @@ int launch_qlinear(const void* x, const void* w, const __half* scales, const int
 // enough work for it, else the single-CTA 128x192 kernel (SAMQ_DENSE=1cta forces the latter)
 int launch_dense(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
                  int64_t M, int K, int N, int epilogue, const RowMap& rowmap, cudaStream_t st) {
-  const char* v = getenv("SAMQ_DENSE");
-  const bool force_1cta = v && strcmp(v, "1cta") == 0;
+  const bool force_1cta = config().dense_1cta;
   if (N % 256 == 0 && M >= 2048 && !force_1cta)
     return launch_dense_pair(x, wt, bias, residual, y, M, K, N, epilogue, rowmap, num_sms(), st);
   return launch_qlinear<192, false>(x, wt, nullptr, nullptr, bias, residual, y, M, K, N, K, epilogue, rowmap, st);
@@ -355,15 +355,17 @@ int qlinear_impl(const char* who, const void* x, const int32_t* qweight, const i
     //                costs more than reading fp16 weights from L2, and the dense GEMM can use the
     //                256x256 CTA-pair tile.  Measured sustained at M = 32768 (tests/gemm_power.py):
     //                fused 870, unpack + pair-dense 1199 TFLOP/s (cuBLAS fp16: 1193).
-    //   fused 2-CTA  (SAMQ_GEMM=2cta): cta_group::2 pair kernel, qlinear2.cu.
-    // SAMQ_GEMM = fused | 2cta | dense forces one of them (ablations, tests).
+    //   fused 2-CTA  (SAMQ_GEMM=2cta, `make ABLATIONS=1` builds only): cta_group::2 pair kernel, qlinear2.cu.
+    // SAMQ_GEMM = fused | dense forces one of the product paths (tests: both must be bit-identical);
+    // resolved once at load (Config, common.cuh), not per call.
     constexpr int64_t kTwoKernelMinM = 12288;
-    const char* variant = getenv("SAMQ_GEMM");
-    const bool force_fused = variant && strcmp(variant, "fused") == 0;
-    const bool force_dense = variant && strcmp(variant, "dense") == 0;
-    if (variant && strcmp(variant, "2cta") == 0 && N % 256 == 0)
+    const int variant = config().gemm;
+    const bool force_fused = variant == 1, force_dense = variant == 2;
+#ifdef SAMQ_ABLATIONS
+    if (variant == 3 && N % 256 == 0)
       return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros, b, r, out, M, K, N,
                                  groupsize, epilogue, rowmap, num_sms(), st);
+#endif
     if (workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0 && !force_fused &&
         (force_dense || M >= kTwoKernelMinM)) {
       rc = unpack_dequant(qweight, qzeros, scales, nullptr, workspace, K, N, 4, groupsize, 1, st);

@@ -1,3 +1,5 @@
+// ABLATION: compiled only with `make ABLATIONS=1` (-DSAMQ_ABLATIONS); not in the shipped libsamq.so.
+#ifdef SAMQ_ABLATIONS
 // 2-CTA (cta_group::2) variant of the fused int4 dequant-GEMM (see qlinear.cu for the
 // single-CTA kernel, the operand orientation and the dequant arithmetic).
 //
@@ -284,3 +286,5 @@ int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales
 }
 
 }  // namespace samq
+
+#endif  // SAMQ_ABLATIONS

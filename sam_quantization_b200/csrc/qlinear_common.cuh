@@ -38,6 +38,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ uint32_t nib_to_h2(uint32_t w) {
   return lop3_and_or(w, 0x000f000fu, 0x64006400u);
 }
+// (a & 0x00f000f0) | 0x54005400  ->  two fp16 values 64 + nibble (nibbles 1 and 5 of the word, unshifted)
+__device__ __forceinline__ uint32_t nib_hi_to_h2(uint32_t w) {
+  return lop3_and_or(w, 0x00f000f0u, 0x54005400u);
+}
 __device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
   asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -260,7 +264,6 @@ __device__ __forceinline__ void dequant_warp_loop(
     const uint32_t z = (zw_next >> zshift) & 0xF;
     const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
     const uint32_t s2 = h2_dup(s);
-    const uint32_t c2 = h2_dup(__hneg(__hmul_rn(s, __float2half(1024.f))));
     const uint32_t nzs2 = h2_dup(__hneg(zs));
     if (kbc + 2 < total_kb) {   // raw loads for the next own k-block: nothing depends on them yet
       p_kb += 2;
@@ -281,12 +284,15 @@ __device__ __forceinline__ void dequant_warp_loop(
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const uint32_t w = q[r];
-      // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q
-      uint32_t a = nib_to_h2(w), b = nib_to_h2(w >> 4), c = nib_to_h2(w >> 8), d = nib_to_h2(w >> 12);
-      a = h2_add(h2_fma(a, s2, c2), nzs2);
-      b = h2_add(h2_fma(b, s2, c2), nzs2);
-      c = h2_add(h2_fma(c, s2, c2), nzs2);
-      d = h2_add(h2_fma(d, s2, c2), nzs2);
+      // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q (even nibbles) / 64+q (odd nibbles, in
+      // place: no shift), minus the magic constant = q exactly, then ONE fma per pair:
+      // fp16(q*s - fp16((z+1)*s)), the rounding of the reference's Triton kernel (fma.rn.f16x2)
+      const uint32_t w8 = w >> 8;
+      uint32_t a = nib_to_h2(w), b = nib_hi_to_h2(w), c = nib_to_h2(w8), d = nib_hi_to_h2(w8);
+      a = h2_fma(h2_add(a, 0xe400e400u), s2, nzs2);   // -1024
+      b = h2_fma(h2_add(b, 0xd400d400u), s2, nzs2);   // -64
+      c = h2_fma(h2_add(c, 0xe400e400u), s2, nzs2);
+      d = h2_fma(h2_add(d, 0xd400d400u), s2, nzs2);
       out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
       out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
       out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)

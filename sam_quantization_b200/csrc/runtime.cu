@@ -173,13 +173,31 @@ int ensure_dynamic_smem(const void* func, int bytes, const char* what) {
   return SAMQ_OK;
 }
 
-bool pdl_enabled(int which) {
-  static const int mask = [] {
-    const char* v = getenv("SAMQ_PDL");     // bit mask of kernel classes launched programmatically
-    return v ? atoi(v) : 0x3;
-  }();
-  return (mask >> which) & 1;
+static Config g_config;
+static std::once_flag g_config_once;
+
+static void load_config() {
+  auto is = [](const char* name, const char* val) {
+    const char* v = getenv(name);
+    return v && strcmp(v, val) == 0;
+  };
+  Config c = {};
+  c.gemm = is("SAMQ_GEMM", "fused") ? 1 : is("SAMQ_GEMM", "dense") ? 2 : is("SAMQ_GEMM", "2cta") ? 3 : 0;
+  c.dense_1cta = is("SAMQ_DENSE", "1cta");
+  c.attn_exact_max = is("SAMQ_ATTN_MAX", "exact");
+  c.attn_win = is("SAMQ_ATTN_WIN", "v1") ? 1 : is("SAMQ_ATTN_WIN", "v2") ? 2 : 0;
+  c.attn_glob = is("SAMQ_ATTN_GLOB", "v1") ? 1 : is("SAMQ_ATTN_GLOB", "v2") ? 2 : 0;
+  const char* pdl = getenv("SAMQ_PDL");
+  c.pdl_mask = pdl ? atoi(pdl) : 0x3;
+  g_config = c;
 }
+
+const Config& config() {
+  std::call_once(g_config_once, load_config);
+  return g_config;
+}
+
+bool pdl_enabled(int which) { return (config().pdl_mask >> which) & 1; }
 
 int device_sm_count() {
   int dev = 0;
@@ -211,7 +229,20 @@ const CUtensorMap* get_tensor_map_2d(const void* base, uint64_t rows, uint64_t c
 // ---------------------------------------------------------------------------
 extern "C" {
 
-int samq_abi_version(void) { return 1; }
+int samq_abi_version(void) { return 2; }
+
+void samq_config_reload(void) {
+  (void)samq::config();
+  samq::load_config();
+}
+
+int samq_has_ablations(void) {
+#ifdef SAMQ_ABLATIONS
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 const char* samq_last_error(void) { return samq::g_err; }
 

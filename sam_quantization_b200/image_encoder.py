@@ -26,14 +26,13 @@ re-layouts + the dense tcgen05 GEMM, LayerNorm2d on the token LayerNorm kernel.
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Tuple, Type
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from .fused_attention import QuantAttention
 from .fused_mlp import QuantMLP
 from .quant_linear import QuantLinear
@@ -216,7 +215,7 @@ class Block(nn.Module):
         if self.window_size > 0:
             ws = self.window_size
             # proj epilogue does window_unpartition + crop + residual: shortcut + unpartition(attn)
-            if ws == 14 and os.environ.get("SAMQ_PAD_SKIP", "1") != "0":   # "0": partition first, multiply the pad rows
+            if ws == 14 and _lib.OPTIONS["pad_skip"]:   # "0": partition first, multiply the pad rows
                 # qkv GEMM does the window_partition in its store, the attention kernel the
                 # window_unpartition in its own: the zero-padding tokens (16 % of the window layout
                 # at 64x64 / 14) are neither normalised nor multiplied by qkv / proj weights
@@ -331,7 +330,7 @@ class ImageEncoderViT(nn.Module):
         C = y.shape[-1]
         if (c3.kernel_size == (3, 3) and c3.stride == (1, 1) and c3.padding == (1, 1) and c3.bias is None
                 and c3.groups == 1 and C % 8 == 0 and (9 * C) % 64 == 0 and c3.out_channels % 256 == 0
-                and os.environ.get("SAMQ_NECK_CONV", "") != "cudnn"):
+                and not _lib.OPTIONS["neck_cudnn"]):
             key = (c3.weight.data_ptr(), c3.weight._version, str(c3.weight.device))
             w3 = self._conv3_cache.get(key)
             if w3 is None:      # [O, C, 3, 3] -> [O, (ky, kx, c)], once per weight version

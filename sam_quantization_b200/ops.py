@@ -7,7 +7,6 @@ and launches the CUDA kernel on torch's current stream.  No eager fallback exist
 from __future__ import annotations
 
 import math
-import os
 from typing import Optional, Tuple
 
 import torch
@@ -86,7 +85,7 @@ def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales
         fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
         # scratch for the dequantised weight: always for the non-int4 formats; for int4 only when
         # M is long enough that the library prefers unpack-once + dense GEMM (see csrc/qlinear.cu)
-        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or os.environ.get("SAMQ_GEMM") == "dense"
+        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense"
         ws = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
         _lib.check(_lib.load().samq_qlinear_fwd(
             _lib.ptr(x2), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx),
@@ -114,7 +113,7 @@ def qlinear_unpartition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Te
     with _dev_ctx(x):
         y = torch.empty_like(shortcut)
         fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
-        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or os.environ.get("SAMQ_GEMM") == "dense"
+        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense"
         wsp = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
         _lib.check(_lib.load().samq_qlinear_unpartition_fwd(
             _lib.ptr(x), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx), _lib.ptr(bias),
@@ -145,7 +144,7 @@ def qlinear_partition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tens
     with _dev_ctx(x):
         y = torch.empty((B * nH * nW, ws, ws, N), dtype=torch.float16, device=x.device)
         fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
-        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or os.environ.get("SAMQ_GEMM") == "dense"
+        need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense"
         wsp = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
         _lib.check(_lib.load().samq_qlinear_partition_fwd(
             _lib.ptr(x), _lib.ptr(qweight), _lib.ptr(qzeros), _lib.ptr(scales), _lib.ptr(g_idx), _lib.ptr(bias),

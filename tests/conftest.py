@@ -40,3 +40,23 @@ def cuda_device():
 
     _lib.device_check(torch.device("cuda:0"))
     return torch.device("cuda:0")
+
+
+@pytest.fixture
+def samq_env(monkeypatch):
+    """Set / unset a SAMQ_* developer switch AND make the library re-read its configuration (the
+    switches are resolved once at load, not per call); everything is restored afterwards."""
+    from sam_quantization_b200 import _lib
+
+    class Env:
+        def set(self, name, value):
+            monkeypatch.setenv(name, value)
+            _lib.reload_config()
+
+        def unset(self, name):
+            monkeypatch.delenv(name, raising=False)
+            _lib.reload_config()
+
+    yield Env()
+    monkeypatch.undo()
+    _lib.reload_config()

@@ -16,11 +16,30 @@ def same_bits(t, ref):
     return np.array_equal(t.cpu().numpy().view(np.uint16), np.ascontiguousarray(ref).view(np.uint16))
 
 
-def test_golden_dequant_fixture(cuda_device, golden_dir):
-    g = np.load(os.path.join(golden_dir, "dequant_b4.npz"))
-    w = ops.unpack_dequant(dev(g["qweight"], cuda_device), dev(g["qzeros"], cuda_device), dev(g["scales"], cuda_device),
-                           4, int(g["groupsize"]))
-    assert same_bits(w, g["w"])
+@pytest.mark.parametrize("tag", ["golden_g128", "golden_nogroups"])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_dequant_equals_the_reference_triton_kernel(cuda_device, golden_dir, tag, transposed):
+    """Bit-equality with the reference's own kernel: the fixture is triton_matmul4(gs, I_K, ...) run
+    on a B200 by oracle/ref_gpu.py (quant_linear.py:355-437).  Both unpack kernels (generic and the
+    transposed int4 fast path that feeds the dense GEMM) are held to it."""
+    g = np.load(os.path.join(golden_dir, "dequant_triton_b4.npz"))
+    w = ops.unpack_dequant(dev(g[f"{tag}_qweight"], cuda_device), dev(g[f"{tag}_qzeros"], cuda_device),
+                           dev(g[f"{tag}_scales"], cuda_device), 4, int(g[f"{tag}_groupsize"]), transposed=transposed)
+    assert same_bits(w.t().contiguous() if transposed else w, g[f"{tag}_w_triton"])
+
+
+@pytest.mark.parametrize("tag", ["golden_g128", "golden_nogroups"])
+def test_fused_gemm_operand_equals_the_reference_triton_kernel(cuda_device, golden_dir, tag, samq_env):
+    """The same identity-matrix extraction through OUR fused in-SM dequant GEMM (the TMEM A operand):
+    qlinear(I_K) must return the Triton kernel's weights bit for bit."""
+    samq_env.set("SAMQ_GEMM", "fused")
+    g = np.load(os.path.join(golden_dir, "dequant_triton_b4.npz"))
+    qw, gs = g[f"{tag}_qweight"], int(g[f"{tag}_groupsize"])
+    K = qw.shape[0] * 8
+    eye = torch.eye(K, dtype=torch.float16, device=cuda_device)
+    w = ops.qlinear(eye, dev(qw, cuda_device), dev(g[f"{tag}_qzeros"], cuda_device), dev(g[f"{tag}_scales"], cuda_device),
+                    4, gs)
+    assert same_bits(w, g[f"{tag}_w_triton"])
 
 
 @pytest.mark.parametrize("bits", [2, 3, 4, 8])

@@ -95,20 +95,20 @@ def test_batch_invariance_and_sharding_property(cuda_device, tmp_path):
 
 
 @pytest.mark.parametrize("batch", [1, 4])
-def test_pad_skipping_block_is_bit_identical(cuda_device, tmp_path, monkeypatch, batch):
+def test_pad_skipping_block_is_bit_identical(cuda_device, tmp_path, samq_env, batch):
     """The windowed block's default form (LayerNorm in image order -> qkv GEMM that partitions in its
     store -> attention that un-partitions in its store -> plain proj GEMM) never multiplies the
     zero-padding tokens of the 70x70 window layout; SAMQ_PAD_SKIP=0 is the reference's order of
     operations (partition, multiply everything, drop).  Same dot products -> identical bits.
     batch 4 takes the unpack-once + CTA-pair GEMM path (M >= 12288), batch 1 the fused kernel."""
-    monkeypatch.delenv("SAMQ_ATTN_WIN", raising=False)   # both forms on the default windowed kernel
+    samq_env.unset("SAMQ_ATTN_WIN")   # both forms on the default windowed kernel
     cfg = dict(embed_dim=640, depth=2, num_heads=8, global_attn_indexes=(1,))
     enc, _ = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=8, device=cuda_device)
     x = torch.from_numpy(synth.tokens_input(batch, 64, 640, seed=9)).half().to(cuda_device)
     with torch.no_grad():
-        monkeypatch.setenv("SAMQ_PAD_SKIP", "0")
+        samq_env.set("SAMQ_PAD_SKIP", "0")
         old = enc.forward_tokens(x)
-        monkeypatch.setenv("SAMQ_PAD_SKIP", "1")
+        samq_env.set("SAMQ_PAD_SKIP", "1")
         new = enc.forward_tokens(x)
     assert torch.equal(old, new)
 

@@ -80,15 +80,15 @@ def test_int4_act_order(cuda_device):
 
 @pytest.mark.parametrize("K,N", [(1280, 3840), (1280, 5120), (5120, 1280)])
 @pytest.mark.parametrize("variant", ["auto", "fused"])
-def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, monkeypatch, K, N, variant):
+def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, samq_env, K, N, variant):
     """At BASELINE's largest M the oracle is replaced by a size-independent identity:
     the fused kernel must equal an fp32 GEMM (torch, on the GPU) of the bit-exact dequantised
     weight (itself pinned to the oracle by test_gpu_dequant)."""
     M = 32768
     if variant == "fused":
-        monkeypatch.setenv("SAMQ_GEMM", "fused")
+        samq_env.set("SAMQ_GEMM", "fused")
     else:
-        monkeypatch.delenv("SAMQ_GEMM", raising=False)
+        samq_env.unset("SAMQ_GEMM")
     qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=8)
     tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
     x = torch.randn(M, K, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(0)).half()
@@ -132,18 +132,20 @@ def test_module_forward_and_reference_entry_point(cuda_device):
 
 @pytest.mark.parametrize("K,N,M", [(1280, 3840, 4900), (5120, 1280, 4096), (1280, 5120, 777)])
 @pytest.mark.parametrize("epilogue", ["none", "gelu"])
-def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, monkeypatch, K, N, M, epilogue):
+def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, samq_env, K, N, M, epilogue):
     """The cta_group::2 kernel (SAMQ_GEMM=2cta) must give bit-identical results to the default
     single-CTA kernel (same operands, same fp32 accumulation order per output)."""
+    if not _lib.has_ablations():
+        pytest.skip("the cta_group::2 fused kernel is only in `make ABLATIONS=1` builds (SAMQ_LIB=...)")
     qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=12)
     tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
     x = torch.randn(M, K, device=cuda_device).half()
     b = torch.randn(N, device=cuda_device).half()
     r = torch.randn(M, N, device=cuda_device).half()
     epi = _lib.EPI_GELU if epilogue == "gelu" else _lib.EPI_NONE
-    monkeypatch.delenv("SAMQ_GEMM", raising=False)
+    samq_env.unset("SAMQ_GEMM")
     y1 = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=epi, residual=r)
-    monkeypatch.setenv("SAMQ_GEMM", "2cta")
+    samq_env.set("SAMQ_GEMM", "2cta")
     y2 = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=epi, residual=r)
     assert torch.equal(y1, y2)
     ref = oq.qlinear(x.cpu().numpy(), qw, qz, sc, 4, 128, b.cpu().numpy(), None, epilogue, r.cpu().numpy())
@@ -152,7 +154,7 @@ def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, monkeypatch, K, N
 
 
 @pytest.mark.parametrize("K,N,gs", [(1280, 1280, 128), (320, 256, 64), (64, 512, 64), (192, 256, 64)])
-def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, monkeypatch, K, N, gs):
+def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, samq_env, K, N, gs):
     """M >= 12288 takes unpack-once + dense GEMM; it must equal the fused kernel bit for bit.
     K = 320, 64, 192: short reductions (fewer k-blocks than pipeline stages, odd counts)."""
     M = 12288 + 77
@@ -160,9 +162,9 @@ def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, monkeypatch, K,
     tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
     x = torch.randn(M, K, device=cuda_device).half()
     b = torch.randn(N, device=cuda_device).half()
-    monkeypatch.delenv("SAMQ_GEMM", raising=False)
+    samq_env.unset("SAMQ_GEMM")
     y_auto = ops.qlinear(x, tq, tz, ts, 4, gs, b, epilogue=_lib.EPI_GELU)
-    monkeypatch.setenv("SAMQ_GEMM", "fused")
+    samq_env.set("SAMQ_GEMM", "fused")
     y_fused = ops.qlinear(x, tq, tz, ts, 4, gs, b, epilogue=_lib.EPI_GELU)
     assert torch.equal(y_auto, y_fused)
     # and the fast transposed int4 dequant kernel is bit-exact against the oracle
@@ -185,14 +187,16 @@ def test_dense_ablation_path_equals_fused(cuda_device):
 @pytest.mark.parametrize("B,H,W,K,N,variant", [(1, 64, 64, 1280, 1280, "auto"), (3, 64, 64, 256, 256, "auto"),
                                                (2, 20, 30, 128, 128, "auto"), (3, 64, 64, 1280, 1280, "dense"),
                                                (2, 64, 64, 768, 768, "2cta")])
-def test_proj_with_fused_unpartition_and_residual(cuda_device, monkeypatch, B, H, W, K, N, variant):
+def test_proj_with_fused_unpartition_and_residual(cuda_device, samq_env, B, H, W, K, N, variant):
     """samq_qlinear_unpartition_fwd == shortcut + window_unpartition(x @ W + bias)
     (image_encoder.py:201-204, 309-333), on every GEMM kernel variant."""
     from oracle import encoder as oe
+    if variant == "2cta" and not _lib.has_ablations():
+        pytest.skip("the cta_group::2 fused kernel is only in `make ABLATIONS=1` builds")
     if variant == "auto":
-        monkeypatch.delenv("SAMQ_GEMM", raising=False)
+        samq_env.unset("SAMQ_GEMM")
     else:
-        monkeypatch.setenv("SAMQ_GEMM", variant)
+        samq_env.set("SAMQ_GEMM", variant)
     ws = 14
     nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
     qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=21)
@@ -213,15 +217,17 @@ def test_proj_with_fused_unpartition_and_residual(cuda_device, monkeypatch, B, H
                                                (2, 20, 30, 128, 384, "auto"), (2, 28, 28, 128, 256, "auto"),
                                                (3, 64, 64, 256, 768, "dense"), (2, 64, 64, 256, 768, "2cta")])
 @pytest.mark.parametrize("with_bias", [True, False])
-def test_qkv_with_fused_partition(cuda_device, monkeypatch, B, H, W, K, N, variant, with_bias):
+def test_qkv_with_fused_partition(cuda_device, samq_env, B, H, W, K, N, variant, with_bias):
     """samq_qlinear_partition_fwd == window_partition(x) @ W + bias (image_encoder.py:196-198,
     282-306) on every GEMM kernel variant -- bit-identical to partitioning first, because the real
     rows see the same dot products and a zero-padding row's result is exactly fp16(0 + bias)."""
     from oracle import encoder as oe
+    if variant == "2cta" and not _lib.has_ablations():
+        pytest.skip("the cta_group::2 fused kernel is only in `make ABLATIONS=1` builds")
     if variant == "auto":
-        monkeypatch.delenv("SAMQ_GEMM", raising=False)
+        samq_env.unset("SAMQ_GEMM")
     else:
-        monkeypatch.setenv("SAMQ_GEMM", variant)
+        samq_env.set("SAMQ_GEMM", variant)
     ws = 14
     qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=44)
     g = torch.Generator().manual_seed(6)

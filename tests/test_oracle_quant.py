@@ -46,6 +46,20 @@ def test_zero_minus_one_quirk_is_reproduced(golden_dir):
     assert z[grp, n] == 15   # (-1) & 0xF: dequant then uses z+1 == 16, not 0
 
 
+@pytest.mark.parametrize("tag", ["golden_g128", "golden_nogroups"])
+def test_dequant_fma_form_is_the_reference_triton_kernel(golden_dir, tag):
+    """The fixture is the output of the reference's OWN kernel on a B200:
+    triton_matmul4(gs, I_K, qweight, scales, qzeros) (quant_linear.py:355-437) run by
+    oracle/ref_gpu.py -- grouped (g128) and NO_GROUPS code paths.  The oracle's default form must
+    reproduce it bit for bit; the un-contracted PyTorch form must not (it is a different rounding)."""
+    g = np.load(os.path.join(golden_dir, "dequant_triton_b4.npz"))
+    args = (g[f"{tag}_qweight"], g[f"{tag}_qzeros"], g[f"{tag}_scales"], 4, int(g[f"{tag}_groupsize"]))
+    assert bits_equal(oq.dequant(*args), g[f"{tag}_w_triton"])
+    assert bits_equal(oq.dequant(*args, form="fma"), g[f"{tag}_w_triton"])
+    step = oq.dequant(*args, form="stepwise")
+    assert np.mean(step.view(np.uint16) != g[f"{tag}_w_triton"].view(np.uint16)) > 0.05
+
+
 def test_dequant_stepwise_is_the_literal_torch_expression(golden_dir):
     g = np.load(os.path.join(golden_dir, "dequant_b4.npz"))
     w = oq.dequant(g["qweight"], g["qzeros"], g["scales"], 4, int(g["groupsize"]), form="stepwise")
