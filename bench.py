@@ -117,45 +117,71 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# CPU baseline = the oracle port of the reference's PyTorch dequant path
+# CPU baseline = the reference's PyTorch dequant path: the reference's OWN
+# ImageEncoderViT (oracle/_ref/segment_anything, staged by oracle/make_ref.py) in fp32 on the host
+# cores, its nn.Linear weights = the dequantised packed weights (what GPTQ.fasterquant writes back,
+# gptq.py:160-162).  kind "reference".  If oracle/_ref was not staged, the oracle's restatement of
+# the same forward runs instead (kind "port").  Nothing here is on the product path.
 # --------------------------------------------------------------------------------------
-def cpu_reference_prepare(model_name: str, packed_state, n_blocks: int):
-    """Oracle-dequantised fp32 weights of the stem, the first ``n_blocks`` blocks and the neck."""
-    from oracle import encoder as oe
+class CpuReference:
+    """Whole encoder, all blocks, ONE image per call (the reference's own batch, gptq4sam_infer.py:223)."""
 
-    sub = {k: v for k, v in packed_state.items()
-           if not k.startswith("blocks.") or int(k.split(".")[1]) < n_blocks}
-    return oe.dequant_state(sub, 4, 128)
+    def __init__(self, model_name: str, packed_state):
+        from oracle import encoder as oe
+        from oracle import make_ref
 
+        self.model_name = model_name
+        self.cfg = oe.CONFIGS[model_name]
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.p = oe.dequant_state(packed_state, 4, 128)
+        self.kind = "port"
+        self.model = None
+        if make_ref.available():
+            make_ref.add_to_path()
+            from functools import partial
 
-def cpu_reference_images_per_s(model_name: str, p, n_blocks: int):
-    """Time ``n_blocks`` consecutive blocks (from block 0: for ViT-H the first 8 blocks have the
-    full model's 7:1 windowed:global mix) + stem + neck of ONE image on the host cores with the
-    oracle, and extrapolate the block time to the full depth.
-    Returns (images/s, seconds per image, cores)."""
-    from oracle import encoder as oe
-    from oracle import synth
+            import segment_anything.modeling.image_encoder as rie   # the staged reference module
 
-    cfg = oe.CONFIGS[model_name]
-    depth = cfg["depth"]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    img = torch.from_numpy(synth.image(1, 1024, seed=0)).half().float()
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        x = torch.nn.functional.conv2d(img, p["patch_embed.proj.weight"], p["patch_embed.proj.bias"], stride=16)
-        x = x.permute(0, 2, 3, 1) + p["pos_embed"]
-        t1 = time.perf_counter()
-        x = oe.tokens_forward(x, p, n_blocks, cfg["num_heads"], 14, cfg["global_attn_indexes"])
-        t2 = time.perf_counter()
-        y = x.permute(0, 3, 1, 2)
-        y = torch.nn.functional.conv2d(y, p["neck.0.weight"])
-        y = oe._layer_norm_2d(y, p["neck.1.weight"], p["neck.1.bias"])
-        y = torch.nn.functional.conv2d(y, p["neck.2.weight"], padding=1)
-        y = oe._layer_norm_2d(y, p["neck.3.weight"], p["neck.3.bias"])
-        t3 = time.perf_counter()
-    sec = (t1 - t0) + (t3 - t2) + (t2 - t1) * depth / n_blocks
-    return 1.0 / sec, sec, cores
+            if model_name != "vit_h":
+                # the shipped partition is hard-coded to ViT-H batch 1 (image_encoder.py:297-305,324-332):
+                # other widths need the generic formulas the reference commented out
+                rie.window_partition = oe.window_partition
+                rie.window_unpartition = oe.window_unpartition
+            c = self.cfg
+            m = rie.ImageEncoderViT(depth=c["depth"], embed_dim=c["embed_dim"], img_size=1024, mlp_ratio=4,
+                                    norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=c["num_heads"],
+                                    patch_size=16, qkv_bias=True, use_rel_pos=True,
+                                    global_attn_indexes=list(c["global_attn_indexes"]), window_size=14, out_chans=256)
+            missing = m.load_state_dict(self.p, strict=False)
+            assert not missing.missing_keys, missing.missing_keys[:4]
+            self.model = m.float().eval()
+            self.kind = "reference"
+            self.p = None
+
+    def describe(self) -> str:
+        d = self.cfg["depth"]
+        if self.kind == "reference":
+            return (f"1 image through the reference's own ImageEncoderViT (all {d} blocks, stem, neck; "
+                    f"oracle/_ref/segment_anything, unmodified) in fp32 torch on all host cores, nn.Linear weights = "
+                    f"the dequantised packed int4 weights (the reference's PyTorch dequant path)")
+        return (f"1 image through the oracle's restatement of the reference encoder (all {d} blocks, stem, neck) in "
+                f"fp32 torch on all host cores with the oracle's dequantised weights (oracle/_ref not staged)")
+
+    def step(self, seed: int = 0) -> float:
+        """Seconds for one image, nothing extrapolated."""
+        from oracle import encoder as oe
+        from oracle import synth
+
+        img = torch.from_numpy(synth.image(1, 1024, seed=seed)).half().float()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            if self.model is not None:
+                self.model(img)
+            else:
+                c = self.cfg
+                oe.encoder(img, self.p, c["depth"], c["num_heads"], c["global_attn_indexes"])
+            return time.perf_counter() - t0
 
 
 def packed_state_cpu(enc):
@@ -201,33 +227,24 @@ def main():
         if rank != 0:
             return
         enc = random_quantized_encoder(args.model, 4, 128, seed=0, device="cpu")
-        state = packed_state_cpu(enc)
+        ref = CpuReference(args.model, packed_state_cpu(enc))
         del enc
-        # size the per-step sample so the whole run ends within a few minutes
-        p1 = cpu_reference_prepare(args.model, state, 1)
+        # one step = ONE whole image (every block; nothing extrapolated): ~4.5 s for ViT-H on 16 cores,
+        # so the driver's --steps 20 --warmup 5 is ~2 minutes
+        for i in range(args.warmup):
+            ref.step(i)
         t0 = time.perf_counter()
-        cpu_reference_images_per_s(args.model, p1, 1)
-        per_block = time.perf_counter() - t0
-        budget = 150.0 / max(1, args.steps + args.warmup)
-        depth = len({k.split(".")[1] for k in state if k.startswith("blocks.")})
-        n_blocks = next((n for n in (8, 4, 2) if n <= depth and per_block * n <= budget), 1)
-        p = cpu_reference_prepare(args.model, state, n_blocks)
-        cores = os.cpu_count() or 1
-        for _ in range(args.warmup):
-            cpu_reference_images_per_s(args.model, p, n_blocks)
-        t0 = time.perf_counter()
-        secs = [cpu_reference_images_per_s(args.model, p, n_blocks)[1] for _ in range(args.steps)]
+        secs = [ref.step(i) for i in range(args.steps)]
         wall = time.perf_counter() - t0
         sec = statistics.mean(secs)
         value = 1.0 / sec
-        sample = (f"per step: 1 image through stem + first {n_blocks} of {depth} blocks + neck, fp32 torch on all host "
-                  f"cores with the oracle's dequantised weights; block time extrapolated to the full depth")
         line = {"impl": "reference", "metric": metric, "value": value, "unit": "images/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": "images/s", "cores": ref.cores, "kind": ref.kind,
+                                 "sample": "per step: " + ref.describe()},
                 "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "wall_s": wall}
+                "wall_s": wall, "s_per_image_min_max": [min(secs), max(secs)]}
         print(json.dumps(line))
         return
 
@@ -242,7 +259,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     _lib.device_check(dev)
-    torch.backends.cudnn.benchmark = True
 
     enc_eager = random_quantized_encoder(args.model, 4, 128, seed=0, device=dev)
     B = args.batch
@@ -257,7 +273,6 @@ def main():
         from sam_quantization_b200.launcher import GraphedEncoder
 
         enc = GraphedEncoder(enc_eager, inputs[0])   # public API: captured forward, replayed per step
-    config["launch"] = "eager" if args.no_graph else "cuda-graph replay of the whole encoder forward"
 
     def barrier():
         if world > 1:
@@ -377,7 +392,9 @@ def main():
             acc[2] += fl
 
     t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    per_rank = [t_ms.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t_ms)       # every rank's own device time: shows what max-over-ranks costs
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t_ms.tolist()
 
@@ -400,6 +417,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 operands, fp32 accumulate (int4 weights dequantised to fp16)",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "launch": "eager" if args.no_graph else "cuda-graph replay of the whole encoder forward",
+            "per_rank_ms_per_step": [round(float(t[0]) / args.steps, 3) for t in per_rank],
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 1024 * 1024 * 2,
                     "d2h_bytes_per_step": B * 256 * 64 * 64 * 2,
                     "api": ("eager forward on host tensors (serial H2D, encoder, D2H)" if args.no_graph else
@@ -425,13 +444,12 @@ def main():
         }
         if not args.no_cpu_baseline:
             try:
-                nb = 8
-                pcpu = cpu_reference_prepare(args.model, packed_state_cpu(enc_eager), nb)
-                ips, sec, cores = cpu_reference_images_per_s(args.model, pcpu, nb)
+                ref = CpuReference(args.model, packed_state_cpu(enc_eager))
+                ref.step(0)                                    # warm-up (thread pool, allocator, page faults)
+                secs = [ref.step(1 + i) for i in range(2)]
                 line["cpu_baseline"] = {
-                    "value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                    "sample": "1 image: stem + first 8 blocks (7 windowed + 1 global) + neck in fp32 torch on the "
-                              "host with the oracle's dequantised weights, block time extrapolated to full depth"}
+                    "value": 1.0 / statistics.mean(secs), "unit": "images/s", "cores": ref.cores, "kind": ref.kind,
+                    "sample": "1 warm-up + 2 timed images, each: " + ref.describe()}
             except Exception as ex:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {ex!r}"}

@@ -328,6 +328,12 @@ def run_encoder(dev, model_name="vit_h"):
     out = {"model": model_name, "protocol": "batch 1, (1,3,1024,1024) fp16, 25 warm-up + 100 iterations, wall clock"}
 
     ours = random_quantized_encoder(model_name, 4, 128, seed=0, device=dev)
+    # random-init weights let the residual stream grow to a few hundred after 32 blocks; the
+    # reference's eager fp16 LayerNorm2d squares (x - mean) in fp16 (common.py:38-43) and would
+    # overflow to inf -> an all-zero embedding.  Shrinking the (linear, bias-free) neck conv1x1 keeps
+    # its input inside fp16's square range without changing what LayerNorm2d then normalises to.
+    with torch.no_grad():
+        ours.neck[0].weight.mul_(1.0 / 32)
     state = {}
     for k, v in ours.state_dict().items():
         state[k.replace(".attn.qkv_proj.", ".attn.qkv.").replace(".attn.o_proj.", ".attn.proj.")] = v.detach().clone()
@@ -389,9 +395,9 @@ def run_encoder(dev, model_name="vit_h"):
         out["parity_ours_vs_reference_gpu"] = {
             "block_outputs": {str(i): compare(our_tokens[i], ref_tokens[i]) for i in probe_blocks},
             "embedding": compare(y, y_ref),
-            "note": "random-init residual stream grows with depth; the reference's eager fp16 LayerNorm2d squares "
-                    "(x - mean) in fp16 (common.py:38-43) and overflows to inf -> 0 output once |x - mean| > 255, "
-                    "so the embedding row is only meaningful when max_ref > 0; block outputs are compared before the neck"}
+            "note": "identical packed weights and input through the reference's own GPU path (Triton QuantLinear + "
+                    "Triton attention + eager fp16 LayerNorm / GELU / residual) and ours; neck conv1x1 weight "
+                    "scaled by 1/32 in both so the reference's fp16 LayerNorm2d does not overflow"}
     t = bench_protocol(ours, inp)
     out["ours_eager_launch_s_per_iter"] = t
     genc = GraphedEncoder(ours, inp)

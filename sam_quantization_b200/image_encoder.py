@@ -301,7 +301,8 @@ class ImageEncoderViT(nn.Module):
                 and conv.weight.dtype == torch.float16 and conv.kernel_size == conv.stride
                 and conv.padding == (0, 0) and conv.kernel_size[0] == conv.kernel_size[1]
                 and conv.kernel_size[0] % 8 == 0 and conv.out_channels % 128 == 0
-                and (conv.in_channels * conv.kernel_size[0] ** 2) % 64 == 0 and conv.bias is not None)
+                and (conv.in_channels * conv.kernel_size[0] ** 2) % 64 == 0 and conv.bias is not None
+                and conv.bias.dtype == torch.float16 and self.pos_embed.dtype == torch.float16)
 
     def _stem_fused(self, x: torch.Tensor) -> torch.Tensor:
         """PatchEmbed + pos_embed as one patch re-layout + one tcgen05 GEMM (bias and the
@@ -310,6 +311,10 @@ class ImageEncoderViT(nn.Module):
         B = x.shape[0]
         P = conv.kernel_size[0]
         Hp, Wp = x.shape[2] // P, x.shape[3] // P
+        if (Hp, Wp) != tuple(self.pos_embed.shape[1:3]) or x.shape[2] % P or x.shape[3] % P:
+            # the eager path's `x + self.pos_embed` fails to broadcast here (image_encoder.py:108-109)
+            raise RuntimeError(f"input of {tuple(x.shape[2:])} pixels gives {Hp}x{Wp} patches, but pos_embed is "
+                               f"{tuple(self.pos_embed.shape[1:3])}")
         rows = ops.patchify(x.contiguous(), P)
         key = (B, self.pos_embed.data_ptr(), self.pos_embed._version, str(x.device))
         pos = self._pos_cache.get(key)

@@ -55,6 +55,36 @@ def unpack_dequant(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Te
     return out
 
 
+def _check_packed(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
+                  g_idx: Optional[torch.Tensor], bias: Optional[torch.Tensor], bits: int, groupsize: int,
+                  K: int, N: int) -> None:
+    """One validation of the packed operands for every QuantLinear entry point: dtype, device,
+    contiguity and the reference's checkpoint shapes (quant_linear.py:96-110): a wrong buffer must
+    be an AssertionError here, never an out-of-bounds device read."""
+    assert qweight.dtype == torch.int32 and qzeros.dtype == torch.int32, "qweight/qzeros must be int32"
+    assert qweight.is_contiguous() and qzeros.is_contiguous(), "qweight/qzeros must be contiguous"
+    _check_half(scales, "scales")
+    assert qweight.dim() == 2 and tuple(qweight.shape) == (K * bits // 32, N), \
+        f"qweight must be [{K * bits // 32}, {N}] (got {tuple(qweight.shape)})"
+    gs = K if groupsize == -1 else groupsize
+    assert gs > 0 and K % gs == 0, "infeatures must be a multiple of groupsize"
+    G = K // gs
+    assert tuple(scales.shape) == (G, N), f"scales must be [{G}, {N}] (got {tuple(scales.shape)})"
+    assert tuple(qzeros.shape) == (G, N * bits // 32), \
+        f"qzeros must be [{G}, {N * bits // 32}] (got {tuple(qzeros.shape)})"
+    tensors = [("qweight", qweight), ("qzeros", qzeros), ("scales", scales)]
+    if g_idx is not None:
+        assert g_idx.dtype == torch.int32 and g_idx.numel() == K and g_idx.is_contiguous(), \
+            "g_idx must be a contiguous int32 vector of infeatures entries"
+        tensors.append(("g_idx", g_idx))
+    if bias is not None:
+        _check_half(bias, "bias")
+        assert bias.numel() == N, "bias must have outfeatures entries"
+        tensors.append(("bias", bias))
+    for name, t in tensors:
+        assert t.device == x.device, f"{name} is on {t.device}, x on {x.device}"
+
+
 def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
             bits: int, groupsize: int, bias: Optional[torch.Tensor] = None,
             g_idx: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_NONE,
@@ -71,9 +101,7 @@ def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales
     N = qweight.shape[1]
     x2 = x.view(-1, K)
     M = x2.shape[0]
-    if bias is not None:
-        _check_half(bias, "bias")
-        assert bias.numel() == N
+    _check_packed(x, qweight, qzeros, scales, g_idx, bias, bits, groupsize, K, N)
     with _dev_ctx(x):
         y = out if out is not None else torch.empty(x.shape[:-1] + (N,), dtype=torch.float16, device=x.device)
         assert y.is_contiguous() and y.dtype == torch.float16 and y.numel() == M * N
@@ -109,7 +137,9 @@ def qlinear_unpartition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Te
     nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
     M = B * nH * nW * ws * ws
     assert x.numel() == M * K, "x must hold every windowed token of the batch"
+    assert x.is_contiguous() and shortcut.is_contiguous()
     assert qweight.shape[1] == N and qweight.shape[0] * 32 // bits == K
+    _check_packed(x, qweight, qzeros, scales, g_idx, bias, bits, groupsize, K, N)
     with _dev_ctx(x):
         y = torch.empty_like(shortcut)
         fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
@@ -137,9 +167,7 @@ def qlinear_partition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tens
     nH, nW = (H + ws - 1) // ws, (W + ws - 1) // ws
     N = qweight.shape[1]
     assert qweight.shape[0] * 32 // bits == K
-    if bias is not None:
-        _check_half(bias, "bias")
-        assert bias.numel() == N
+    _check_packed(x, qweight, qzeros, scales, g_idx, bias, bits, groupsize, K, N)
     M = B * H * W
     with _dev_ctx(x):
         y = torch.empty((B * nH * nW, ws, ws, N), dtype=torch.float16, device=x.device)
@@ -162,6 +190,14 @@ def dense_linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor]
     assert x.shape[-1] == K
     x2 = x.view(-1, K)
     M = x2.shape[0]
+    if bias is not None:
+        _check_half(bias, "bias")
+        assert bias.numel() == N and bias.device == x.device, "bias must be fp16[N] on x's device"
+    if residual is not None:
+        _check_half(residual, "residual")
+        assert residual.numel() == M * N and residual.device == x.device, \
+            f"residual must hold M*N = {M * N} fp16 values (got {residual.numel()})"
+    assert wt.device == x.device
     with _dev_ctx(x):
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float16, device=x.device)
         if M == 0:

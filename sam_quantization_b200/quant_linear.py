@@ -21,6 +21,8 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import warnings
+
 import torch
 import torch.nn as nn
 
@@ -155,10 +157,19 @@ class QuantLinear(nn.Module):
         dev = self.qweight.device
         self.qweight = pack_fields(intweight, self.bits).contiguous().to(dev)
         zeros_m1 = (zeros_t - 1).to(torch.int32)
+        if bool((zeros_m1 < 0).any()):
+            # zero == 0 is not representable: the checkpoint stores zero-1 (gptq4sam.py:484), the
+            # reference packs the -1 unmasked and its sign bits overwrite the neighbouring columns'
+            # zero points.  Bug-compatible bits are kept (tests pin them), but say so.
+            warnings.warn(f"QuantLinear.pack: {int((zeros_m1 < 0).sum())} group zero points are 0; the reference's "
+                          f"`zero - 1` storage cannot hold them and corrupts neighbouring qzeros fields "
+                          f"(use sym=True or a Quantizer whose grid keeps zero >= 1)", RuntimeWarning)
         self.qzeros = pack_fields(zeros_m1.t().contiguous(), self.bits).t().contiguous().to(dev)
         self.scales = scales_t.to(torch.float16).to(dev)
-        if self.bias is not None and lbias is not None:
-            self.bias = lbias.detach().clone().to(torch.float16).to(dev)
+        if self.bias is not None:
+            # a bare weight tensor carries no bias: zero it instead of leaving torch.empty garbage
+            self.bias = (torch.zeros(n, dtype=torch.float16) if lbias is None
+                         else lbias.detach().clone().to(torch.float16)).to(dev)
         self.g_idx = None if g_idx is None else gi.to(torch.int32).to(dev)
 
     def extra_repr(self) -> str:

@@ -179,11 +179,52 @@ def make_encoder_fixture():
     print("encoder fixture", y.shape, float(np.abs(y).max()))
 
 
+def make_encoder_q4_fixture():
+    """The benchmarked configuration's numerics at ViT-H width: reference ImageEncoderViT (depth 2,
+    batch 1, fp32, unpatched) whose block Linears hold the DEQUANTISED int4-g128 weights -- the
+    reference's PyTorch dequant path -- on the image the CUDA test feeds
+    through the packed weights.  Everything is derived from seeds, so only outputs are stored."""
+    from functools import partial
+
+    from oracle import encoder as oe
+    from segment_anything.modeling.image_encoder import ImageEncoderViT
+
+    cfg = dict(embed_dim=1280, depth=2, num_heads=16, global_attn_indexes=(1,))
+    enc = ImageEncoderViT(img_size=1024, patch_size=16, embed_dim=1280, depth=2, num_heads=16, mlp_ratio=4,
+                          out_chans=256, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                          use_rel_pos=True, window_size=14, global_attn_indexes=(1,))
+    p = synth.fp_state(seed=7, **cfg)
+    rng = np.random.default_rng(23)
+    for k in p:
+        if "rel_pos" in k:
+            p[k] = (rng.standard_normal(p[k].shape) * 0.2).astype(np.float32)
+    state = oe.dequant_state(synth.to_torch(synth.quantize_state(p, 4, 128)), 4, 128)
+    enc.load_state_dict(state, strict=True)
+    img = synth.image(1, 1024, seed=7).astype(np.float16).astype(np.float32)
+    grabbed = {}
+    hooks = [enc.blocks[i].register_forward_hook(lambda _m, _i, o, i=i: grabbed.__setitem__(i, o.detach().numpy()))
+             for i in range(2)]
+    with torch.no_grad():
+        y = enc(torch.from_numpy(img)).numpy()
+    for h in hooks:
+        h.remove()
+    np.savez_compressed(os.path.join(HERE, "encoder_vith_d2_q4.npz"), y_sub=y[:, :, ::4, ::4].astype(np.float32),
+                        y_mean=np.float64(y.mean()), y_absmax=np.float64(np.abs(y).max()),
+                        tok0_sub=grabbed[0][:, ::4, ::4, ::8].astype(np.float32), tok0_absmax=np.float64(np.abs(grabbed[0]).max()),
+                        tok1_sub=grabbed[1][:, ::4, ::4, ::8].astype(np.float32), tok1_absmax=np.float64(np.abs(grabbed[1]).max()),
+                        seed=7, relpos_seed=23, bits=4, groupsize=128)
+    print("encoder q4 fixture", y.shape, float(np.abs(y).max()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder_q4":
+        make_encoder_q4_fixture()
+        sys.exit(0)
     torch.manual_seed(0)
     make_pack_fixtures()
     make_dequant_fixture()
     make_attention_fixture()
     make_partition_fixture()
     make_encoder_fixture()
+    make_encoder_q4_fixture()
     print("done")
