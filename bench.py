@@ -126,7 +126,7 @@ class ClockSampler:
 class CpuReference:
     """Whole encoder, all blocks, ONE image per call (the reference's own batch, gptq4sam_infer.py:223)."""
 
-    def __init__(self, model_name: str, packed_state):
+    def __init__(self, model_name: str, packed_state, bits: int = 4):
         from oracle import encoder as oe
         from oracle import make_ref
 
@@ -134,7 +134,7 @@ class CpuReference:
         self.cfg = oe.CONFIGS[model_name]
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
-        self.p = oe.dequant_state(packed_state, 4, 128)
+        self.p = oe.dequant_state(packed_state, bits, 128)
         self.kind = "port"
         self.model = None
         if make_ref.available():
@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32,
                     help="images per GPU per step (BASELINE config 3 is a batch sweep: 8 / 16 / 32 / 64 per GPU give "
                          "179 / 182 / 185 / 188 images/s on one B200)")
+    ap.add_argument("--bits", type=int, default=4, choices=[2, 3, 4, 8],
+                    help="weight bits (BASELINE config 4: 3 and 8 with --act-order)")
+    ap.add_argument("--act-order", action="store_true", help="permutation-derived g_idx (non-contiguous groups)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
@@ -212,8 +215,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric = f"SAM {args.model.replace('_', '-').upper().replace('VIT', 'ViT')} GPTQ-int4 encoder images/s"
-    config = {"workload": f"SAM {args.model} image encoder, GPTQ int4 groupsize 128, random-init packed weights, "
+    fmt = f"int{args.bits}" + ("-actorder" if args.act_order else "")
+    metric = f"SAM {args.model.replace('_', '-').upper().replace('VIT', 'ViT')} GPTQ-{fmt} encoder images/s"
+    config = {"workload": f"SAM {args.model} image encoder, GPTQ int{args.bits} groupsize 128"
+                          f"{' with act-order g_idx' if args.act_order else ''}, random-init packed weights, "
                           f"synthetic 1024x1024 images, batch {args.batch}/GPU/step",
               "global_batch": args.batch * world, "parallelism": f"dp{world} (replicas, no data-path collective)",
               "l2": "no explicit flush: the working set of one step (packed weights + activations of the batch, "
@@ -226,8 +231,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        enc = random_quantized_encoder(args.model, 4, 128, seed=0, device="cpu")
-        ref = CpuReference(args.model, packed_state_cpu(enc))
+        enc = random_quantized_encoder(args.model, args.bits, 128, seed=0, device="cpu", act_order=args.act_order)
+        ref = CpuReference(args.model, packed_state_cpu(enc), args.bits)
         del enc
         # one step = ONE whole image (every block; nothing extrapolated): ~4.5 s for ViT-H on 16 cores,
         # so the driver's --steps 20 --warmup 5 is ~2 minutes
@@ -260,7 +265,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     _lib.device_check(dev)
 
-    enc_eager = random_quantized_encoder(args.model, 4, 128, seed=0, device=dev)
+    enc_eager = random_quantized_encoder(args.model, args.bits, 128, seed=0, device=dev, act_order=args.act_order)
     B = args.batch
     nbuf = 3
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -444,7 +449,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             try:
-                ref = CpuReference(args.model, packed_state_cpu(enc_eager))
+                ref = CpuReference(args.model, packed_state_cpu(enc_eager), args.bits)
                 ref.step(0)                                    # warm-up (thread pool, allocator, page faults)
                 secs = [ref.step(1 + i) for i in range(2)]
                 line["cpu_baseline"] = {

@@ -96,6 +96,15 @@ int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
                         int K, int N, int bits, int groupsize, int transposed,
                         void* stream);
 
+/* Column gather  y[m, j] = x[m, perm[j]]  (x, y fp16 [M, K], perm int32 [K]).
+ * No reference counterpart as a kernel: the reference's QuantLinear has no g_idx
+ * (quant_linear.py:66-116); GPTQ act-order checkpoints (gptq.py:88-96 permute the
+ * columns before rounding) store g_idx[k] = group of input feature k.  The host
+ * sorts qweight's rows by group once (QuantLinear.sorted_pack) and gathers x with
+ * this kernel, so that the fused in-SM dequant GEMM sees contiguous groups. */
+int samq_gather_cols_fwd(const void* x, const int32_t* perm, void* y, int64_t M, int K,
+                         void* stream);
+
 /* Dequant-GEMM ---------------------------------------------------------------
  * Replaces triton_matmul4 + matmul4_kernel + the separate bias add
  * (quant_linear.py:231-352, 355-437), with optional fused GELU (common.py:26)
@@ -103,12 +112,12 @@ int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
  *   y[M,N] = epi( x[M,K] . W[K,N] + bias[N] ) + residual[M,N]
  * x, y, residual fp16 row-major; bias fp16 [N] or NULL; residual NULL or [M,N]
  * (may alias y).  fp32 accumulation on tcgen05 tensor cores.
- * bits == 4 with g_idx == NULL and groupsize % 64 == 0 runs the fused
- * unpack->TMEM->tcgen05 kernel when M < 12288 or workspace == NULL; for longer M
- * (where re-dequantising the weight tile for every 192-token tile costs more than
- * reading fp16 weights from L2) and for every other format (bits 2/3/8, g_idx) it
- * runs unpack_dequant into `workspace` (K*N fp16 device scratch, may be reused
- * between calls on the same stream) followed by the dense tcgen05 kernel.
+ * bits 2/3/4/8 with g_idx == NULL and groupsize % 64 == 0 run the fused
+ * unpack-in-registers->TMEM->tcgen05 kernel when M < 12288 or workspace == NULL; for
+ * longer M (where re-dequantising the weight tile for every 192-token tile costs more
+ * than reading fp16 weights from L2) and whenever g_idx != NULL it runs unpack_dequant
+ * into `workspace` (K*N fp16 device scratch, may be reused between calls on the same
+ * stream) followed by the dense tcgen05 kernel.
  * Requires K % 64 == 0, N % 128 == 0 (the reference asserts K % 128 == 0 and
  * N % 256 == 0, quant_linear.py:389-395). */
 int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,

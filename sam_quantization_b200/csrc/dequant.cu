@@ -1,11 +1,12 @@
 // Standalone unpack + dequantise of GPTQ-packed weights (HBM-bound).
 //
-// Arithmetic follows the reference kernel literally (quant_linear.py:334-339):
+// Arithmetic follows the reference kernel (quant_linear.py:334-339) as Triton compiles it on
+// this GPU (enable_fp_fusion: mul.f16x2 for the zero term, fma.rn.f16x2 for the rest):
 //     zeros = (z + 1) * scales         -> fp16 rounding
-//     b     = q * scales - zeros       -> fp16 rounding after the product and after
-//                                         the subtraction (no FMA contraction)
-// which is what PyTorch produces for the same expression on fp16 tensors; the
-// oracle (oracle/quant.py, dequant form "stepwise") is the bit-exact checker.
+//     b     = fma(q, scales, -zeros)   -> ONE fp16 rounding
+// pinned by the identity-matrix extraction from triton_matmul4 on the B200
+// (tests/golden/dequant_triton_b4.npz); the oracle (oracle/quant.py, dequant form "fma") is the
+// bit-exact checker.
 //
 // Packing (gptq4sam.py:472-495): 2/4/8-bit fields LSB-first, 32/bits consecutive
 // k per int32 of qweight[k/f, n]; 32/bits consecutive n per int32 of
@@ -219,7 +220,51 @@ int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* sc
   }
 }
 
+// ---- column gather for act-order layers on the fused GEMM path --------------------------------
+// y[m, j] = x[m, perm[j]]: with the rows of qweight sorted by group (host, once per checkpoint)
+// the fused kernel sees contiguous groups and x its columns in the same order.  One warp per row:
+// the row is staged in shared memory with 16-byte loads, each lane assembles 16-byte outputs.
+__global__ void __launch_bounds__(256)
+gather_cols_kernel(const __half* __restrict__ x, const int32_t* __restrict__ perm, __half* __restrict__ y,
+                   int64_t M, int K) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __half* rows = reinterpret_cast<__half*>(gsm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* row = rows + static_cast<size_t>(warp) * K;
+  for (int64_t m = static_cast<int64_t>(blockIdx.x) * 8 + warp; m < M; m += static_cast<int64_t>(gridDim.x) * 8) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + m * K);
+    for (int c = lane; c < K / 8; c += 32) reinterpret_cast<uint4*>(row)[c] = src[c];
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(y + m * K);
+    for (int c = lane; c < K / 8; c += 32) {
+      const int4 p0 = reinterpret_cast<const int4*>(perm)[2 * c], p1 = reinterpret_cast<const int4*>(perm)[2 * c + 1];
+      __align__(16) __half v[8] = {row[p0.x], row[p0.y], row[p0.z], row[p0.w], row[p1.x], row[p1.y], row[p1.z], row[p1.w]};
+      dst[c] = *reinterpret_cast<const uint4*>(v);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace samq
+
+extern "C" int samq_gather_cols_fwd(const void* x, const int32_t* perm, void* y, int64_t M, int K, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(x && perm && y && x != y, SAMQ_ERR_BAD_ARG, "samq_gather_cols_fwd: null or aliased pointer");
+  SAMQ_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && K <= 8192, SAMQ_ERR_BAD_SHAPE,
+               "samq_gather_cols_fwd: M=%lld K=%d (K must be a multiple of 8, at most 8192)", (long long)M, K);
+  SAMQ_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(perm) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "samq_gather_cols_fwd: pointers must be 16-byte aligned");
+  const int smem = 8 * K * 2;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gather_cols_kernel), smem, "gather_cols"); rc != SAMQ_OK)
+    return rc;
+  const int64_t blocks = (M + 7) / 8;
+  const int grid = static_cast<int>(blocks < 148 * 8 ? blocks : 148 * 8);
+  gather_cols_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), perm, reinterpret_cast<__half*>(y), M, K);
+  count_launch();
+  return check_launch("gather_cols_kernel");
+}
 
 extern "C" int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
                                    const void* scales, const int32_t* g_idx, void* w_out, int K,

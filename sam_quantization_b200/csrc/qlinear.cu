@@ -50,18 +50,19 @@ constexpr int kBN = 128;        // output features per tile (UMMA M)
 constexpr int kBK = 64;         // k per pipeline stage (one 128-byte swizzle row of fp16)
 constexpr int kThreads = 448;   // 14 warps, see the role table above
 constexpr int kWarpTma = 12, kWarpMma = 13;
-constexpr int kWStageBytes = 8 * kBN * 4;   // packed int4 tile: 8 words x 128 n
 constexpr int kAStageBytes = kBN * kBK * 2; // dense fp16 Wt tile
 
-template <int BM, bool FUSED>
+template <int BM, bool FUSED, int BITS = 4>
 struct Cfg {
+  static constexpr int kWStageBytes = 2 * BITS * kBN * 4;   // packed tile of one k-block: 2*BITS words x 128 n
   static constexpr int kXStageBytes = BM * kBK * 2;
   static constexpr int kXStages = FUSED ? 6 : 5;
-  static constexpr int kWStages = 8;                        // fused only
+  static constexpr int kWStages = BITS == 8 ? 4 : 8;        // fused only (8-bit tiles are 8 KB each)
   static constexpr int kAStages = (512 - 2 * BM) / 32;      // TMEM A stages (fused only)
   static constexpr int kTmemABase = 2 * BM;                 // column offset of A stages
   static constexpr int kSmemData =
       kXStages * kXStageBytes + (FUSED ? kWStages * kWStageBytes : kXStages * kAStageBytes);
+  static_assert(kSmemData + 4 * 2048 + 1024 + 512 <= 232448, "shared memory budget");
   static constexpr int kEpiBytes = 4 * 2048;  // one 32x32 fp16 transpose block per epilogue warp
   static constexpr int kNumBars = 2 * kXStages + 2 * kWStages + 2 * 8 + 4;
   static constexpr int kSmemBytes = kSmemData + kEpiBytes + kNumBars * 8 + 16 + 1024;  // + alignment slack
@@ -69,13 +70,14 @@ struct Cfg {
   static_assert(BM % 32 == 0 && BM <= 256, "BM");
 };
 
-template <int BM, bool FUSED, bool GELU>
+template <int BM, bool FUSED, bool GELU, int BITS = 4>
 __global__ void __launch_bounds__(kThreads, 1)
 qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N,
                int K, int groupsize, const RowMap rowmap) {
-  using C = Cfg<BM, FUSED>;
+  using C = Cfg<BM, FUSED, BITS>;
+  constexpr int kWStageBytes = C::kWStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -147,7 +149,7 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // packed weights first: the dequant warps are the longer leg of the pipeline
             mbar_wait(&w_empty[ws], wph ^ 1);
             mbar_arrive_expect_tx(&w_full[ws], kWStageBytes);
-            tma_load_2d(sw + ws * kWStageBytes, &map_w, &w_full[ws], n_tile * kBN, kb * 8);
+            tma_load_2d(sw + ws * kWStageBytes, &map_w, &w_full[ws], n_tile * kBN, kb * 2 * BITS);
             if (++ws == C::kWStages) { ws = 0; wph ^= 1; }
           }
           mbar_wait(&x_empty[xs], xph ^ 1);
@@ -224,7 +226,7 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // quadrant) take alternate k-blocks, so one set's unpack + tcgen05.st latency (~500 clk
     // per k-block for a single warp) hides behind the other's and behind the 384-clk MMA.
     if (FUSED) {
-      dequant_warp_loop<C::kWStages, C::kAStages, kWStageBytes>(
+      dequant_warp_loop<C::kWStages, C::kAStages, kWStageBytes, BITS>(
           warp >> 3, warp & 3, lane, total_kb, num_kb, N, groupsize, scales, qzeros, sw, w_full, w_empty,
           a_empty, tmem_base + C::kTmemABase,
           [&](int tl) { return ((static_cast<int>(blockIdx.x) + tl * static_cast<int>(gridDim.x)) % NT) * kBN; },
@@ -276,18 +278,18 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
 int num_sms() { return device_sm_count(); }
 
-template <int BM, bool FUSED>
+template <int BM, bool FUSED, int BITS = 4>
 int launch_qlinear(const void* x, const void* w, const __half* scales, const int32_t* qzeros,
                    const __half* bias, const __half* residual, __half* y, int64_t M, int K, int N,
                    int groupsize, int epilogue, const RowMap& rowmap, cudaStream_t st) {
-  using C = Cfg<BM, FUSED>;
+  using C = Cfg<BM, FUSED, BITS>;
   const CUtensorMap* mx = get_tensor_map_2d(x, static_cast<uint64_t>(M), K, static_cast<uint64_t>(K) * 2, BM, kBK, 2, 3);
   if (!mx) return SAMQ_ERR_LAUNCH;
   const CUtensorMap* mw =
-      FUSED ? get_tensor_map_2d(w, K / 8, N, static_cast<uint64_t>(N) * 4, 8, kBN, 4, 0)
+      FUSED ? get_tensor_map_2d(w, static_cast<uint64_t>(K) * BITS / 32, N, static_cast<uint64_t>(N) * 4, 2 * BITS, kBN, 4, 0)
             : get_tensor_map_2d(w, N, K, static_cast<uint64_t>(K) * 2, kBN, kBK, 2, 3);
   if (!mw) return SAMQ_ERR_LAUNCH;
-  auto kern = epilogue == SAMQ_EPI_GELU ? qlinear_kernel<BM, FUSED, true> : qlinear_kernel<BM, FUSED, false>;
+  auto kern = epilogue == SAMQ_EPI_GELU ? qlinear_kernel<BM, FUSED, true, BITS> : qlinear_kernel<BM, FUSED, false, BITS>;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "qlinear_kernel"); rc != SAMQ_OK) return rc;
   const int NT = N / kBN;
   const int64_t MT = (M + BM - 1) / BM;
@@ -343,37 +345,46 @@ int qlinear_impl(const char* who, const void* x, const int32_t* qweight, const i
   const __half* b = reinterpret_cast<const __half*>(bias);
   const __half* r = reinterpret_cast<const __half*>(residual);
   __half* out = reinterpret_cast<__half*>(y);
-  const bool fused = bits == 4 && g_idx == nullptr && groupsize % kBK == 0 &&
-                     reinterpret_cast<uintptr_t>(qweight) % 16 == 0;
+  // The fused kernel (unpack in registers -> TMEM A operand -> MMA) exists for every packing
+  // (template parameter BITS of qlinear_kernel / unpack_kblock); it needs contiguous groups of a
+  // multiple of 64 k.  Act-order checkpoints (g_idx) reach it through the host, which sorts the
+  // rows of qweight by group once and gathers the columns of x (ops.py / QuantLinear.sorted_pack).
+  const bool fused = g_idx == nullptr && groupsize % kBK == 0 && reinterpret_cast<uintptr_t>(qweight) % 16 == 0 &&
+                     (bits != 3 || (K % 32 == 0 && N % 32 == 0)) && N % (bits == 3 ? 32 : 32 / bits) == 0;
   if (fused) {
-    // Kernel choice for int4 (all sm_100a, all tcgen05):
+    // Kernel choice (all sm_100a, all tcgen05):
     //   fused 1-CTA  (default for M < kTwoKernelMinM): unpack in registers -> TMEM -> MMA.  Weight
-    //                bytes stay int4 all the way, which is what matters while the GEMM is short.
+    //                bytes stay packed all the way, which is what matters while the GEMM is short.
     //   unpack-once + dense GEMM (default for M >= kTwoKernelMinM when a workspace is given):
     //                every 128x192 tile of the fused kernel re-dequantises its weight tile, i.e.
     //                M/192 times per weight; for long M that redundant ALU work (and its power)
     //                costs more than reading fp16 weights from L2, and the dense GEMM can use the
     //                256x256 CTA-pair tile.  Measured sustained at M = 32768 (tests/gemm_power.py):
     //                fused 870, unpack + pair-dense 1199 TFLOP/s (cuBLAS fp16: 1193).
-    //   fused 2-CTA  (SAMQ_GEMM=2cta, `make ABLATIONS=1` builds only): cta_group::2 pair kernel, qlinear2.cu.
+    //   fused 2-CTA  (SAMQ_GEMM=2cta, `make ABLATIONS=1` builds only, int4): cta_group::2 pair kernel, qlinear2.cu.
     // SAMQ_GEMM = fused | dense forces one of the product paths (tests: both must be bit-identical);
     // resolved once at load (Config, common.cuh), not per call.
     constexpr int64_t kTwoKernelMinM = 12288;
     const int variant = config().gemm;
     const bool force_fused = variant == 1, force_dense = variant == 2;
 #ifdef SAMQ_ABLATIONS
-    if (variant == 3 && N % 256 == 0)
+    if (variant == 3 && N % 256 == 0 && bits == 4)
       return launch_qlinear_pair(x, qweight, reinterpret_cast<const __half*>(scales), qzeros, b, r, out, M, K, N,
                                  groupsize, epilogue, rowmap, num_sms(), st);
 #endif
     if (workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0 && !force_fused &&
         (force_dense || M >= kTwoKernelMinM)) {
-      rc = unpack_dequant(qweight, qzeros, scales, nullptr, workspace, K, N, 4, groupsize, 1, st);
+      rc = unpack_dequant(qweight, qzeros, scales, nullptr, workspace, K, N, bits, groupsize, 1, st);
       if (rc != SAMQ_OK) return rc;
       return launch_dense(x, workspace, b, r, out, M, K, N, epilogue, rowmap, st);
     }
-    return launch_qlinear<192, true>(x, qweight, reinterpret_cast<const __half*>(scales), qzeros, b, r, out, M,
-                                     K, N, groupsize, epilogue, rowmap, st);
+    const __half* sc = reinterpret_cast<const __half*>(scales);
+    switch (bits) {
+      case 2: return launch_qlinear<192, true, 2>(x, qweight, sc, qzeros, b, r, out, M, K, N, groupsize, epilogue, rowmap, st);
+      case 3: return launch_qlinear<192, true, 3>(x, qweight, sc, qzeros, b, r, out, M, K, N, groupsize, epilogue, rowmap, st);
+      case 8: return launch_qlinear<192, true, 8>(x, qweight, sc, qzeros, b, r, out, M, K, N, groupsize, epilogue, rowmap, st);
+      default: return launch_qlinear<192, true, 4>(x, qweight, sc, qzeros, b, r, out, M, K, N, groupsize, epilogue, rowmap, st);
+    }
   }
   SAMQ_REQUIRE(workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, SAMQ_ERR_BAD_ARG,
                "%s: bits=%d%s needs a 16-byte aligned K*N fp16 workspace", who, bits, g_idx ? " with g_idx" : "");

@@ -34,6 +34,32 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-(poly * e), ax, fmaxf(x, 0.f));
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction) ----
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_dup(float v) { return f32x2_pack(v, v); }
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // (a & 0x000f000f) | 0x64006400  ->  two fp16 values 1024 + nibble
 __device__ __forceinline__ uint32_t nib_to_h2(uint32_t w) {
   return lop3_and_or(w, 0x000f000fu, 0x64006400u);
@@ -139,37 +165,54 @@ struct EpiBlock {
         asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + j * 64), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
       }
     } else {
-      // gelu_erf() over the 32 tokens, software-pipelined by hand in three stages so that the
-      // two MUFU ops of an element (rcp, ex2: one warp-instruction per 8 clk each) are spread
-      // between the ~12 FMA-pipe instructions of its neighbours instead of being issued as two
-      // bursts of 32 (volatile asm keeps the order)
-      float ax[32], tt[32], pe[32];
+      // gelu_erf() over the 32 tokens, two tokens per instruction: Blackwell's packed fp32 pipe
+      // (fma.rn.f32x2 = two IEEE fp32 FMAs per issue slot) halves the FMA-pipe instruction count
+      // of the polynomial, which is what the lin1 GEMM loses tensor cycles to (the GELU warps
+      // took 45 % of the SM's issue slots; the MMA-issuing warp was `not_selected` 22 % of its
+      // samples).  Same formula as gelu_erf(); max(x, 0) is formed exactly as 0.5 |x| + 0.5 x so
+      // that it needs no scalar max.  Software-pipelined by hand in three stages so that the four
+      // MUFU ops of a pair (2 rcp, 2 ex2: one warp-instruction per 8 clk each) are spread between
+      // the packed FMA-pipe instructions of its neighbours (volatile asm keeps the order).
+      const uint64_t bv2 = f32x2_dup(bv);
+      const uint64_t kP = f32x2_dup(0.3275911f * 0.70710678118654752440f), kOne = f32x2_dup(1.0f);
+      const uint64_t kC4 = f32x2_dup(-0.5f * 1.061405429f), kC3 = f32x2_dup(-0.5f * -1.453152027f);
+      const uint64_t kC2 = f32x2_dup(-0.5f * 1.421413741f), kC1 = f32x2_dup(-0.5f * -0.284496736f);
+      const uint64_t kC0 = f32x2_dup(-0.5f * 0.254829592f), kHalf = f32x2_dup(0.5f);
+      const uint64_t kNU2 = f32x2_dup(-0.72134752044448170368f);   // -log2(e) / 2:  exp(-x^2/2) = 2^(kNU2 x^2)
+      uint64_t xv[16], av[16], tv[16], qv[16];
 #pragma unroll
-      for (int j = 0; j < 34; ++j) {
-        if (j < 32) {
-          ax[j] = __uint_as_float(r[j]) + bv;           // v (sign kept), |v| via fabsf below
-          const float d = fmaf(fabsf(ax[j]), 0.3275911f * 0.70710678118654752440f, 1.0f);
-          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(tt[j]) : "f"(d));
+      for (int j = 0; j < 18; ++j) {
+        if (j < 16) {
+          xv[j] = f32x2_add(f32x2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), bv2);
+          av[j] = xv[j] & 0x7fffffff7fffffffull;                  // |x|
+          float d0, d1, t0, t1;
+          f32x2_unpack(f32x2_fma(av[j], kP, kOne), d0, d1);
+          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+          tv[j] = f32x2_pack(t0, t1);
         }
-        if (j >= 1 && j < 33) {
+        if (j >= 1 && j < 17) {
           const int i = j - 1;
-          const float t = tt[i], a = fabsf(ax[i]);
-          float poly = 0.5f * 1.061405429f;
-          poly = fmaf(poly, t, 0.5f * -1.453152027f);
-          poly = fmaf(poly, t, 0.5f * 1.421413741f);
-          poly = fmaf(poly, t, 0.5f * -0.284496736f);
-          poly = fmaf(poly, t, 0.5f * 0.254829592f);
-          poly *= t;
-          const float u = a * 0.84932180028801904272f;  // |x| * sqrt(log2(e) / 2)
-          float e;
-          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
-          pe[i] = poly * e;
+          const uint64_t t = tv[i];
+          uint64_t poly = f32x2_fma(kC4, t, kC3);                 // -(0.5 erfc polynomial), Horner
+          poly = f32x2_fma(poly, t, kC2);
+          poly = f32x2_fma(poly, t, kC1);
+          poly = f32x2_fma(poly, t, kC0);
+          poly = f32x2_mul(poly, t);
+          float w0, w1, e0, e1;
+          f32x2_unpack(f32x2_mul(f32x2_mul(xv[i], xv[i]), kNU2), w0, w1);
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
+          qv[i] = f32x2_mul(poly, f32x2_pack(e0, e1));            // -g
         }
         if (j >= 2) {
           const int i = j - 2;
-          const float v = ax[i];
-          const float g = fmaf(-pe[i], fabsf(v), fmaxf(v, 0.f));
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + i * 64), "h"(__half_as_ushort(__float2half_rn(g))) : "memory");
+          float g0, g1;
+          const uint64_t relu = f32x2_fma(av[i], kHalf, f32x2_mul(xv[i], kHalf));   // exact
+          f32x2_unpack(f32x2_fma(av[i], qv[i], relu), g0, g1);
+          const __half2 h = __floats2half2_rn(g0, g1);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + (2 * i) * 64), "h"(__half_as_ushort(__low2half(h))) : "memory");
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(wr + (2 * i + 1) * 64), "h"(__half_as_ushort(__high2half(h))) : "memory");
         }
       }
     }
@@ -214,6 +257,76 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// ---- in-register unpack of one k-block (64 k) of ONE output feature -> 32 fp16 pairs (k, k+1) ----
+// `q` holds the thread's 2*BITS packed words of the k-block (GPTQ layout: fields LSB-first along k,
+// 32/BITS per word; 3-bit: 32 fields as a 96-bit little-endian stream over 3 words, quant.py:160-180).
+// Every format goes through the same two fp16 steps as dequant.cu, on pairs:
+//   q = (1024 + q) - 1024  (exact: the field is OR-ed into the mantissa of 1024.0),
+//   w = fma(q, s, -fp16((z+1) s))  -- the rounding of the reference's Triton kernel.
+template <int BITS>
+__device__ __forceinline__ void unpack_kblock(const uint32_t (&q)[2 * BITS], uint32_t s2, uint32_t nzs2,
+                                              uint32_t (&out)[32]) {
+  if constexpr (BITS == 4) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t w = q[r];
+      // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q (even nibbles) / 64+q (odd nibbles, in
+      // place: no shift), minus the magic constant = q exactly, then ONE fma per pair
+      const uint32_t w8 = w >> 8;
+      uint32_t a = nib_to_h2(w), b = nib_hi_to_h2(w), c = nib_to_h2(w8), d = nib_hi_to_h2(w8);
+      a = h2_fma(h2_add(a, 0xe400e400u), s2, nzs2);   // -1024
+      b = h2_fma(h2_add(b, 0xd400d400u), s2, nzs2);   // -64
+      c = h2_fma(h2_add(c, 0xe400e400u), s2, nzs2);
+      d = h2_fma(h2_add(d, 0xd400d400u), s2, nzs2);
+      out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
+      out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
+      out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)
+      out[4 * r + 3] = prmt(c, d, 0x7632);  // (k6,k7)
+    }
+  } else if constexpr (BITS == 8) {
+    // a word is 4 consecutive k as bytes: prmt interleaves them with 0x64 -> fp16 1024 + byte
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const uint32_t lo = prmt(q[r], 0x64646464u, 0x4140), hi = prmt(q[r], 0x64646464u, 0x4342);
+      out[2 * r + 0] = h2_fma(h2_add(lo, 0xe400e400u), s2, nzs2);   // (k0,k1)
+      out[2 * r + 1] = h2_fma(h2_add(hi, 0xe400e400u), s2, nzs2);   // (k2,k3)
+    }
+  } else if constexpr (BITS == 2) {
+    // a word is 16 consecutive k: (w >> 2j) & 0x00030003 = fields j and j + 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        h[j] = h2_fma(h2_add(lop3_and_or(q[r] >> (2 * j), 0x00030003u, 0x64006400u), 0xe400e400u), s2, nzs2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        out[8 * r + j] = prmt(h[2 * j], h[2 * j + 1], 0x5410);       // (k_2j, k_2j+1)
+        out[8 * r + 4 + j] = prmt(h[2 * j], h[2 * j + 1], 0x7632);   // (k_8+2j, k_8+2j+1)
+      }
+    }
+  } else {
+    static_assert(BITS == 3, "bits");
+    // 32 fields per 3 words; field i sits at bit 3 i of the 96-bit stream (fields 10 and 21 straddle)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int pr = 0; pr < 16; ++pr) {
+        uint32_t f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int bit = 3 * (2 * pr + e), word = bit >> 5, off = bit & 31;
+          uint32_t v = q[3 * c + word] >> off;
+          if (off + 3 > 32) v |= q[3 * c + word + 1] << (32 - off);
+          f[e] = v & 7u;
+        }
+        const uint32_t h = (f[0] | (f[1] << 16)) | 0x64006400u;
+        out[16 * c + pr] = h2_fma(h2_add(h, 0xe400e400u), s2, nzs2);
+      }
+    }
+  }
+}
+
 // One dequant warp's main loop (shared by the 1-CTA and 2-CTA kernels).
 //
 // `set` (0/1) takes the CTA-wide k-blocks kbc = set, set+2, ...  For each of them the warp
@@ -223,16 +336,24 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 //   arrive_full(as) -> signal "A stage written" to the MMA issuer (local or remote barrier)
 // No integer division on the per-k-block path: (tile, kb, group) are tracked incrementally
 // (two dependent runtime divisions per k-block cost ~250 clk of latency in the first version).
-template <int kWStages, int kAStages, int kWStageBytes, class NOfTile, class ArriveFull>
+template <int kWStages, int kAStages, int kWStageBytes, int BITS = 4, class NOfTile, class ArriveFull>
 __device__ __forceinline__ void dequant_warp_loop(
     int set, int q4, int lane, int total_kb, int num_kb, int N, int groupsize,
     const __half* __restrict__ scales, const int32_t* __restrict__ qzeros, const uint8_t* sw,
     uint64_t* w_full, uint64_t* w_empty, uint64_t* a_empty, uint32_t tmem_a_base,
     NOfTile n_of_tile, ArriveFull arrive_full) {
   static_assert((kWStages & (kWStages - 1)) == 0 && (kAStages & (kAStages - 1)) == 0, "ring sizes");
+  static_assert(kWStageBytes == 2 * BITS * 128 * 4, "packed tile = 2*BITS words x 128 features");
   const int tid = q4 * 32 + lane;  // 0..127 == TMEM lane == feature within the CTA's tile
-  const int zwords = N / 8;
-  const int zshift = (tid & 7) * 4;
+  // zero point of feature n: field n of the qzeros row (same packing as the weights, along n).
+  // A tile starts at a multiple of 128 features, so the field's place inside its word (or, for
+  // 3 bits, inside its 3-word chunk) depends on tid only.
+  constexpr int kFieldsPerWord = BITS == 3 ? 1 : 32 / BITS;
+  const int zwords = BITS == 3 ? N / 32 * 3 : N / kFieldsPerWord;
+  const int zbit = BITS == 3 ? 3 * (tid & 31) : (tid % kFieldsPerWord) * BITS;
+  const int zword_in_tile = BITS == 3 ? (tid >> 5) * 3 + (zbit >> 5) : tid / kFieldsPerWord;
+  const int zshift = zbit & 31;
+  const bool zstraddle = BITS == 3 && zshift + 3 > 32;
   const int kb_per_group = groupsize / 64;
 
   // cursor of the k-block whose constants are being PREFETCHED (one own-k-block ahead)
@@ -243,11 +364,14 @@ __device__ __forceinline__ void dequant_warp_loop(
   };
   normalise();
   __half s_next = __float2half(0.f);
-  uint32_t zw_next = 0;
+  uint32_t zw_next = 0, zw_next_hi = 0;
   auto prefetch = [&]() {
-    const int n = n_of_tile(p_tl) + tid;
-    s_next = scales[static_cast<int64_t>(p_g) * N + n];
-    zw_next = static_cast<uint32_t>(qzeros[static_cast<int64_t>(p_g) * zwords + (n >> 3)]);
+    const int n0 = n_of_tile(p_tl);
+    s_next = scales[static_cast<int64_t>(p_g) * N + n0 + tid];
+    const int32_t* zp = qzeros + static_cast<int64_t>(p_g) * zwords +
+                        (BITS == 3 ? n0 / 32 * 3 : n0 / kFieldsPerWord) + zword_in_tile;
+    zw_next = static_cast<uint32_t>(zp[0]);
+    if (BITS == 3 && zstraddle) zw_next_hi = static_cast<uint32_t>(zp[1]);
   };
   if (set < total_kb) prefetch();
 
@@ -261,7 +385,9 @@ __device__ __forceinline__ void dequant_warp_loop(
     const bool a_ready = mbar_test(&a_empty[as], aph ^ 1);
 
     const __half s = s_next;
-    const uint32_t z = (zw_next >> zshift) & 0xF;
+    uint32_t z = zw_next >> zshift;
+    if (BITS == 3 && zstraddle) z |= zw_next_hi << (32 - zshift);
+    z &= (1u << BITS) - 1u;
     const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
     const uint32_t s2 = h2_dup(s);
     const uint32_t nzs2 = h2_dup(__hneg(zs));
@@ -274,30 +400,14 @@ __device__ __forceinline__ void dequant_warp_loop(
 
     if (!w_ready) mbar_wait(&w_full[ws], wph);
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(sw + ws * kWStageBytes) + tid;
-    uint32_t q[8];
+    uint32_t q[2 * BITS];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) q[r] = wp[r * 128];
+    for (int r = 0; r < 2 * BITS; ++r) q[r] = wp[r * 128];
     __syncwarp();
     if (lane == 0) mbar_arrive(&w_empty[ws]);
 
     uint32_t out[32];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const uint32_t w = q[r];
-      // (k0,k4) (k1,k5) (k2,k6) (k3,k7) as fp16 pairs 1024+q (even nibbles) / 64+q (odd nibbles, in
-      // place: no shift), minus the magic constant = q exactly, then ONE fma per pair:
-      // fp16(q*s - fp16((z+1)*s)), the rounding of the reference's Triton kernel (fma.rn.f16x2)
-      const uint32_t w8 = w >> 8;
-      uint32_t a = nib_to_h2(w), b = nib_hi_to_h2(w), c = nib_to_h2(w8), d = nib_hi_to_h2(w8);
-      a = h2_fma(h2_add(a, 0xe400e400u), s2, nzs2);   // -1024
-      b = h2_fma(h2_add(b, 0xd400d400u), s2, nzs2);   // -64
-      c = h2_fma(h2_add(c, 0xe400e400u), s2, nzs2);
-      d = h2_fma(h2_add(d, 0xd400d400u), s2, nzs2);
-      out[4 * r + 0] = prmt(a, b, 0x5410);  // (k0,k1)
-      out[4 * r + 1] = prmt(c, d, 0x5410);  // (k2,k3)
-      out[4 * r + 2] = prmt(a, b, 0x7632);  // (k4,k5)
-      out[4 * r + 3] = prmt(c, d, 0x7632);  // (k6,k7)
-    }
+    unpack_kblock<BITS>(q, s2, nzs2, out);
     if (!a_ready) mbar_wait(&a_empty[as], aph ^ 1);   // MMAs that read this A stage are done
     tc_fence_after();
     tmem_st_x32(tmem_a_base + as * 32 + (static_cast<uint32_t>(q4 * 32) << 16), out);

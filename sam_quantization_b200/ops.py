@@ -85,6 +85,24 @@ def _check_packed(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, 
         assert t.device == x.device, f"{name} is on {t.device}, x on {x.device}"
 
 
+def gather_cols(x: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """``x[..., perm]`` for fp16 ``x[..., K]`` and an int32 permutation of ``K`` entries
+    (act-order layers on the fused GEMM path, see ``QuantLinear.sorted_pack``)."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x")
+    K = x.shape[-1]
+    assert perm.dtype == torch.int32 and perm.numel() == K and perm.is_contiguous() and perm.device == x.device, \
+        "perm must be a contiguous int32 vector of K entries on x's device"
+    M = x.numel() // K
+    with _dev_ctx(x):
+        y = torch.empty_like(x)
+        if M == 0:
+            return y
+        _lib.check(_lib.load().samq_gather_cols_fwd(_lib.ptr(x), _lib.ptr(perm), _lib.ptr(y), M, K,
+                                                    _lib.stream_ptr(x.device)))
+    return y
+
+
 def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
             bits: int, groupsize: int, bias: Optional[torch.Tensor] = None,
             g_idx: Optional[torch.Tensor] = None, epilogue: int = _lib.EPI_NONE,
@@ -110,7 +128,7 @@ def qlinear(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales
             assert residual.numel() == M * N
         if M == 0:
             return y
-        fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
+        fused = g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
         # scratch for the dequantised weight: always for the non-int4 formats; for int4 only when
         # M is long enough that the library prefers unpack-once + dense GEMM (see csrc/qlinear.cu)
         need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense"
@@ -142,7 +160,7 @@ def qlinear_unpartition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Te
     _check_packed(x, qweight, qzeros, scales, g_idx, bias, bits, groupsize, K, N)
     with _dev_ctx(x):
         y = torch.empty_like(shortcut)
-        fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
+        fused = g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
         need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense"
         wsp = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
         _lib.check(_lib.load().samq_qlinear_unpartition_fwd(
@@ -171,7 +189,7 @@ def qlinear_partition(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tens
     M = B * H * W
     with _dev_ctx(x):
         y = torch.empty((B * nH * nW, ws, ws, N), dtype=torch.float16, device=x.device)
-        fused = bits == 4 and g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
+        fused = g_idx is None and (K if groupsize == -1 else groupsize) % 64 == 0
         need_ws = (not fused) or M >= TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense"
         wsp = torch.empty(K * N, dtype=torch.float16, device=x.device) if need_ws else None
         _lib.check(_lib.load().samq_qlinear_partition_fwd(

@@ -28,7 +28,8 @@ import torch.nn as nn
 
 from . import _lib, ops
 
-__all__ = ["QuantLinear", "make_quant", "matmul4", "triton_matmul4", "autotune_warmup", "pack_fields"]
+__all__ = ["QuantLinear", "make_quant", "matmul4", "triton_matmul4", "autotune_warmup", "pack_fields",
+           "unpack_fields"]
 
 
 def pack_fields(vals: torch.Tensor, bits: int) -> torch.Tensor:
@@ -68,6 +69,30 @@ def pack_fields(vals: torch.Tensor, bits: int) -> torch.Tensor:
     return words.to(torch.int32)
 
 
+def unpack_fields(words: torch.Tensor, bits: int) -> torch.Tensor:
+    """Inverse of :func:`pack_fields` for properly masked fields: int32 words ``[R, C]`` ->
+    int64 fields ``[R * 32 / bits, C]`` (CPU; one-time checkpoint re-layout only)."""
+    w = words.detach().cpu().to(torch.int64) & 0xFFFFFFFF
+    rows, cols = w.shape
+    if bits in (2, 4, 8):
+        f = 32 // bits
+        out = torch.stack([(w >> (bits * j)) & ((1 << bits) - 1) for j in range(f)], dim=1)
+        return out.reshape(rows * f, cols)
+    if bits == 3:
+        assert rows % 3 == 0
+        w = w.view(rows // 3, 3, cols)
+        fields = []
+        for j in range(32):
+            p = 3 * j
+            word, off = p // 32, p % 32
+            v = w[:, word] >> off
+            if off + 3 > 32:
+                v = v | (w[:, word + 1] << (32 - off))
+            fields.append(v & 7)
+        return torch.stack(fields, dim=1).reshape(rows // 3 * 32, cols)
+    raise NotImplementedError("Only 2,3,4,8 bits are supported.")
+
+
 class QuantLinear(nn.Module):
     """GPTQ-packed linear layer (reference: quant_linear.py:66-116)."""
 
@@ -104,19 +129,65 @@ class QuantLinear(nn.Module):
         self.register_buffer("g_idx", None)
 
     # ------------------------------------------------------------------ forward
+    def sorted_pack(self):
+        """Act-order layers on the fused in-SM dequant path: ``(perm, qweight_sorted)`` with the
+        input features re-ordered so that every group is contiguous -- ``perm = argsort(g_idx)``
+        (stable), ``qweight_sorted`` = the same integer fields, rows ``perm`` -- so that
+        ``x[:, perm] @ dequant(qweight_sorted, contiguous groups) == x @ dequant(qweight, g_idx)``
+        (same products, summed in a different order).  Needs every group to have exactly
+        ``groupsize`` members, which GPTQ's act-order guarantees (``g_idx = invperm // groupsize``);
+        returns ``None`` otherwise.  Computed once per weight version (CPU re-pack), cached."""
+        if self.g_idx is None:
+            return None
+        key = (self.qweight.data_ptr(), self.qweight._version, self.g_idx.data_ptr(), self.g_idx._version)
+        hit = getattr(self, "_sorted_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        g = self.g_idx.detach().cpu().to(torch.int64)
+        groups = self.infeatures // self.groupsize
+        ok = (self.infeatures % self.groupsize == 0 and int(g.min()) >= 0 and int(g.max()) < groups
+              and bool((torch.bincount(g, minlength=groups) == self.groupsize).all()))
+        result = None
+        if ok:
+            perm = torch.argsort(g, stable=True)
+            fields = unpack_fields(self.qweight, self.bits)[perm]
+            dev = self.qweight.device
+            result = (perm.to(torch.int32).to(dev), pack_fields(fields, self.bits).contiguous().to(dev))
+        self._sorted_cache = (key, result)
+        return result
+
+    def _use_sorted(self, rows: int):
+        """(perm, qweight_sorted) when the call should take gather + fused kernel, else None."""
+        if self.g_idx is None or rows >= ops.TWO_KERNEL_MIN_M or _lib.OPTIONS["gemm"] == "dense" \
+                or self.groupsize % 64 != 0:
+            return None
+        return self.sorted_pack()
+
     def forward(self, x: torch.Tensor, epilogue: int = _lib.EPI_NONE,
                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        sp = self._use_sorted(x.numel() // max(1, x.shape[-1])) if x.is_cuda else None
+        if sp is not None:      # act-order, short M: gather x's columns, contiguous groups, fused kernel
+            return ops.qlinear(ops.gather_cols(x, sp[0]), sp[1], self.qzeros, self.scales, self.bits,
+                               self.groupsize, self.bias, None, epilogue, residual)
         return ops.qlinear(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
                            self.bias, self.g_idx, epilogue, residual)
 
     def forward_unpartition(self, x: torch.Tensor, shortcut: torch.Tensor, window_size: int) -> torch.Tensor:
         """``shortcut + window_unpartition(self(x))`` in one kernel (x: windowed tokens)."""
+        sp = self._use_sorted(x.numel() // max(1, x.shape[-1])) if x.is_cuda else None
+        if sp is not None:
+            return ops.qlinear_unpartition(ops.gather_cols(x, sp[0]), sp[1], self.qzeros, self.scales, self.bits,
+                                           self.groupsize, self.bias, shortcut, window_size, None)
         return ops.qlinear_unpartition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
                                        self.bias, shortcut, window_size, self.g_idx)
 
     def forward_partition(self, x: torch.Tensor, window_size: int) -> torch.Tensor:
         """``self(window_partition(x))`` in one kernel: ``x[B, H, W, K]`` in image order ->
         ``[B*nWin, ws, ws, N]``; the zero-padding tokens are not multiplied (their rows = bias)."""
+        sp = self._use_sorted(x.numel() // max(1, x.shape[-1])) if x.is_cuda else None
+        if sp is not None:
+            return ops.qlinear_partition(ops.gather_cols(x, sp[0]), sp[1], self.qzeros, self.scales, self.bits,
+                                         self.groupsize, self.bias, window_size, None)
         return ops.qlinear_partition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
                                      self.bias, window_size, self.g_idx)
 

@@ -16,10 +16,18 @@ __all__ = ["randomize_packed_", "random_quantized_encoder"]
 
 
 @torch.no_grad()
-def randomize_packed_(model: nn.Module, seed: int = 0, scale_lo: float = 0.003, scale_hi: float = 0.006) -> None:
+def randomize_packed_(model: nn.Module, seed: int = 0, scale_lo: float = 0.003, scale_hi: float = 0.006,
+                      act_order: bool = False) -> None:
+    """``act_order``: also give every layer a permutation-derived ``g_idx`` (``invperm // groupsize``,
+    what GPTQ's act-order produces: non-contiguous groups of exactly ``groupsize`` members)."""
     g = torch.Generator().manual_seed(seed)
     for m in model.modules():
         if isinstance(m, QuantLinear):
+            if act_order:
+                perm = torch.randperm(m.infeatures, generator=g)
+                inv = torch.empty_like(perm)
+                inv[perm] = torch.arange(m.infeatures)
+                m.g_idx = (inv // m.groupsize).to(torch.int32)
             m.qweight.copy_(torch.randint(-2**31, 2**31 - 1, m.qweight.shape, generator=g, dtype=torch.int64).to(torch.int32))
             m.qzeros.copy_(torch.randint(-2**31, 2**31 - 1, m.qzeros.shape, generator=g, dtype=torch.int64).to(torch.int32))
             m.scales.copy_((torch.rand(m.scales.shape, generator=g) * (scale_hi - scale_lo) + scale_lo).half())
@@ -47,13 +55,14 @@ def _materialize_meta_(model: nn.Module, seed: int) -> None:
 
 
 def random_quantized_encoder(name: str = "vit_h", bits: int = 4, groupsize: int = 128, seed: int = 0,
-                             device: str = "cuda", relw_mode: str = "reference", **overrides) -> ImageEncoderViT:
+                             device: str = "cuda", relw_mode: str = "reference", act_order: bool = False,
+                             **overrides) -> ImageEncoderViT:
     torch.manual_seed(seed)
     with torch.device("meta"):          # skip the 2.5 GB fp32 init of Linear weights that get replaced
         enc = build_image_encoder(name, **overrides)
     make_quant(enc, bits, groupsize)
     _materialize_meta_(enc, seed)
-    randomize_packed_(enc, seed)
+    randomize_packed_(enc, seed, act_order=act_order)
     enc = enc.half()
     make_quant_attn(enc, relw_mode=relw_mode)
     make_fused_mlp(enc)

@@ -15,9 +15,13 @@ def gelu_as(x):
     for c in (-1.453152027, 1.421413741, -0.284496736, 0.254829592):
         poly = (poly * t + np.float32(0.5 * c)).astype(np.float32)
     poly = (poly * t).astype(np.float32)
-    u = (ax * np.float32(0.84932180028801904272)).astype(np.float32)
-    e = np.exp2(-(u * u).astype(np.float32)).astype(np.float32)
-    return (np.maximum(x, 0) - (poly * e).astype(np.float32) * ax).astype(np.float32)
+    # the epilogue's packed-fp32 form (qlinear_common.cuh::EpiBlock::finish):
+    #   e = 2^((x x) (-log2(e)/2)),  g = poly e,  relu = 0.5 |x| + 0.5 x (exact),  gelu = fma(|x|, -g, relu)
+    e = np.exp2(((x * x).astype(np.float32) * np.float32(-0.72134752044448170368)).astype(np.float32)).astype(np.float32)
+    g = (poly * e).astype(np.float32)
+    relu = (ax * np.float32(0.5) + x * np.float32(0.5)).astype(np.float32)
+    assert np.array_equal(relu, np.maximum(x, 0))
+    return (relu.astype(np.float64) - ax.astype(np.float64) * g).astype(np.float32)
 
 
 def test_gelu_formula_error_is_below_fp16_resolution():
@@ -30,4 +34,4 @@ def test_gelu_formula_error_is_below_fp16_resolution():
     ratio = err / ulp16
     assert ratio.max() < 1.0                       # never more than one fp16 ulp (far negative tail, |y| < 2e-4)
     assert ratio[np.abs(ref) >= 1e-2].max() < 0.05  # invisible everywhere the output is not tiny
-    assert abs(0.84932180028801904272 - math.sqrt(math.log2(math.e) / 2)) < 1e-15
+    assert abs(0.72134752044448170368 - math.log2(math.e) / 2) < 1e-15

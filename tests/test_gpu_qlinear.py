@@ -241,3 +241,68 @@ def test_qkv_with_fused_partition(cuda_device, samq_env, B, H, W, K, N, variant,
     ref = ops.qlinear(xw.to(cuda_device), *packed, bd)
     assert y.shape == ref.shape
     assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("bits", [2, 3, 8])
+@pytest.mark.parametrize("gs", [128, 64, -1])
+def test_fused_in_sm_unpack_of_every_format_is_bit_exact(cuda_device, samq_env, bits, gs):
+    """The fused kernel's in-register unpackers (qlinear_common.cuh::unpack_kblock<2|3|8>): the
+    identity-matrix extraction qlinear(I_K) must return the oracle's dequantised weight bit for bit,
+    exactly as for int4 (which is pinned to the Triton kernel in test_gpu_dequant)."""
+    samq_env.set("SAMQ_GEMM", "fused")
+    K, N = 512, 384
+    g = K if gs == -1 else gs
+    qw, qz, sc, _ = rand_packed(K, N, bits, g, seed=20 + bits, scale_lo=1e-4)
+    eye = torch.eye(K, dtype=torch.float16, device=cuda_device)
+    launches = _lib.launch_count()
+    w = ops.qlinear(eye, dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device), bits, gs)
+    assert _lib.launch_count() - launches == 1            # one kernel: no unpack pass
+    ref = oq.dequant(qw, qz, sc, bits, g)
+    assert np.array_equal(w.cpu().numpy().view(np.uint16), ref.view(np.uint16))
+
+
+@pytest.mark.parametrize("bits", [2, 3, 8])
+@pytest.mark.parametrize("M,K,N", [(196, 1280, 3840), (4096, 1280, 1280), (1000, 5120, 1280)])
+def test_fused_and_unpack_once_paths_agree_for_every_format(cuda_device, samq_env, bits, M, K, N):
+    """BASELINE config 4/5 formats on ViT-H layer shapes: the fused in-SM dequant GEMM against the
+    oracle, and against the unpack-once + dense GEMM path on the same operands (same k order in the
+    tensor core: identical bits)."""
+    samq_env.set("SAMQ_GEMM", "fused")
+    run_case(cuda_device, M, K, N, bits, 128, seed=30 + bits)
+    qw, qz, sc, _ = rand_packed(K, N, bits, 128, seed=40 + bits)
+    x = torch.randn(M, K, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(1)).half()
+    b = torch.randn(N, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(2)).half()
+    args = (dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device), bits, 128, b)
+    y_fused = ops.qlinear(x, *args, epilogue=_lib.EPI_GELU)
+    samq_env.set("SAMQ_GEMM", "dense")
+    y_dense = ops.qlinear(x, *args, epilogue=_lib.EPI_GELU)
+    assert torch.equal(y_fused, y_dense)
+
+
+@pytest.mark.parametrize("bits", [3, 4, 8])
+def test_act_order_layer_takes_gather_plus_fused_kernel(cuda_device, samq_env, bits):
+    """QuantLinear with a g_idx at short M: rows of qweight sorted by group once (sorted_pack), x's
+    columns gathered (samq_gather_cols_fwd), fused in-SM dequant kernel on contiguous groups.  Same
+    products as the g_idx-aware unpack + dense path, summed in another order: both within the GEMM
+    tolerance of the oracle, and within two output ulps of each other."""
+    samq_env.unset("SAMQ_GEMM")
+    K, N, gs, M = 1280, 1280, 128, 600
+    qw, qz, sc, gi = rand_packed(K, N, bits, gs, seed=50 + bits, g_idx=True)
+    layer = sq.QuantLinear(bits, gs, K, N, bias=True)
+    rng = np.random.default_rng(5)
+    bias = rng.standard_normal(N).astype(np.float16)
+    layer.qweight, layer.qzeros, layer.scales = (torch.from_numpy(a) for a in (qw, qz, sc))
+    layer.bias = torch.from_numpy(bias)
+    layer.g_idx = torch.from_numpy(gi)
+    layer = layer.to(cuda_device)
+    x = rng.standard_normal((M, K)).astype(np.float16)
+    xd = dev(x, cuda_device)
+    launches = _lib.launch_count()
+    y = layer(xd)
+    assert _lib.launch_count() - launches == 2            # gather + fused GEMM (no unpack pass)
+    assert torch.equal(ops.gather_cols(xd, layer.sorted_pack()[0]), xd[:, layer.sorted_pack()[0].long()])
+    ref = oq.qlinear(x, qw, qz, sc, bits, gs, bias, gi)
+    err, mag, cos = report(y, ref)
+    assert err <= ULP * mag + 1e-6 and cos >= 0.99999
+    y_dense = ops.qlinear(xd, layer.qweight, layer.qzeros, layer.scales, bits, gs, layer.bias, layer.g_idx)
+    assert (y.float() - y_dense.float()).abs().max().item() <= 2 * ULP * mag

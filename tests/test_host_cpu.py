@@ -206,3 +206,39 @@ def test_matmul4_reference_assertions():
     with pytest.raises(AssertionError):
         sq.triton_matmul4(128, a, torch.zeros(16, 256, dtype=torch.int32), torch.zeros(1, 256, dtype=torch.float16),
                           torch.zeros(1, 32, dtype=torch.int32))
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4, 8])
+def test_unpack_fields_inverts_pack_fields(bits):
+    from sam_quantization_b200.quant_linear import unpack_fields
+
+    g = torch.Generator().manual_seed(bits)
+    vals = torch.randint(0, 2 ** bits, (96, 40), generator=g)
+    assert torch.equal(unpack_fields(pack_fields(vals, bits), bits), vals)
+
+
+@pytest.mark.parametrize("bits", [3, 4, 8])
+def test_sorted_pack_of_an_act_order_layer_is_the_same_weight(bits):
+    """QuantLinear.sorted_pack: rows of qweight re-ordered so that groups are contiguous.  Checked
+    with the oracle: dequant(sorted, contiguous groups) == dequant(original, g_idx)[perm], bit for bit."""
+    K, N, gs = 256, 64, 64
+    rng = np.random.default_rng(bits)
+    layer = sq.QuantLinear(bits, gs, K, N, bias=False)
+    qw = rng.integers(-2**31, 2**31, size=tuple(layer.qweight.shape), dtype=np.int64).astype(np.int32)
+    qz = rng.integers(-2**31, 2**31, size=tuple(layer.qzeros.shape), dtype=np.int64).astype(np.int32)
+    sc = rng.uniform(0.002, 0.02, size=tuple(layer.scales.shape)).astype(np.float16)
+    perm0 = rng.permutation(K)
+    inv = np.empty(K, dtype=np.int64)
+    inv[perm0] = np.arange(K)
+    gi = (inv // gs).astype(np.int32)
+    layer.qweight, layer.qzeros, layer.scales = torch.from_numpy(qw), torch.from_numpy(qz), torch.from_numpy(sc)
+    assert layer.sorted_pack() is None                       # no g_idx: nothing to sort
+    layer.g_idx = torch.from_numpy(gi)
+    perm, qw_sorted = layer.sorted_pack()
+    assert layer.sorted_pack()[1] is qw_sorted               # cached
+    w = oq.dequant(qw, qz, sc, bits, gs, gi)
+    w_sorted = oq.dequant(qw_sorted.numpy(), qz, sc, bits, gs)
+    assert np.array_equal(w_sorted.view(np.uint16), w[perm.numpy()].view(np.uint16))
+    assert np.array_equal(np.sort(gi[perm.numpy()]), gi[perm.numpy()])   # groups contiguous and ascending
+    layer.g_idx = torch.from_numpy(np.minimum(gi, 1))        # unequal group sizes: not sortable into gs-blocks
+    assert layer.sorted_pack() is None
