@@ -96,6 +96,29 @@ int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
                         int K, int N, int bits, int groupsize, int transposed,
                         void* stream);
 
+/* GPTQ calibration (offline solver) ---------------------------
+ * Hessian accumulation, replaces GPTQ.add_batch (gptq.py:29-60: `self.H *= n/(n+1);
+ * inp = sqrt(2/(n+1)) inp.float(); self.H += inp.matmul(inp.t())`) on the tensor cores:
+ *   h[m, n] = beta h[m, n] + alpha sum_t at[m, t] bt[n, t]
+ * at, bt fp16 [n_feat, tokens] row-major (the layer input TRANSPOSED, zero-padded to
+ * tokens % 64 == 0; bt may equal at; any n_feat), h fp32 [n_feat, n_feat], fp32 accumulation.
+ * fp32 inputs are fed as an fp16 split x = hi + 2^-11 lo (three calls: hi.hi, hi.lo,
+ * lo.hi), which restores fp32 accuracy; see sam_quantization_b200/gptq.py. */
+int samq_syrk_f32_fwd(const void* at, const void* bt, void* h, int n_feat, int64_t tokens,
+                      float alpha, float beta, void* stream);
+
+/* One column block of GPTQ.fasterquant's inner loop (gptq.py:108-141), all rows in
+ * parallel, columns sequential.  For i in [0, ncols):  with (s, z) = scale/zero[r, colmap[i]]
+ *   q = s (clamp(round(w_i / s) + z, 0, maxq) - z);  Q[r, col0+i] = q;
+ *   e = (w_i - q) / U[col0+i, col0+i];  E[r, i] = e;  loss += (w_i - q)^2 / U_ii^2 / 2;
+ *   w_j -= e U[col0+i, col0+j]  for j >= i (inside the block only)
+ * W fp32 [rows, ldw] (read only: the block-entry values), U fp32 [ldu, ldu] upper Cholesky
+ * factor of H^-1, scale / zero fp32 [rows, nparams], colmap int32 [ncols], Q fp32
+ * [rows, ldq], E fp32 [rows, ncols], loss fp32 scalar (accumulated).  ncols <= 128. */
+int samq_gptq_block_fwd(void* W, int ldw, int rows, int col0, int ncols, const void* U, int ldu,
+                        const void* scale, const void* zero, int nparams, const int32_t* colmap,
+                        int maxq, void* Q, int ldq, void* E, void* loss, void* stream);
+
 /* Column gather  y[m, j] = x[m, perm[j]]  (x, y fp16 [M, K], perm int32 [K]).
  * No reference counterpart as a kernel: the reference's QuantLinear has no g_idx
  * (quant_linear.py:66-116); GPTQ act-order checkpoints (gptq.py:88-96 permute the

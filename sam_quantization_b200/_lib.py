@@ -42,6 +42,12 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     ),
+    "samq_syrk_f32_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_void_p]),
+    "samq_gptq_block_fwd": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+         c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    ),
     "samq_gather_cols_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "samq_qlinear_fwd": (
         c_int,

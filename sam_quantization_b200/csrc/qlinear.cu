@@ -70,12 +70,15 @@ struct Cfg {
   static_assert(BM % 32 == 0 && BM <= 256, "BM");
 };
 
-template <int BM, bool FUSED, bool GELU, int BITS = 4>
+// F32ACC (dense mode only): the epilogue writes  y32[m, n] = alpha * acc + beta * y32[m, n]  in fp32
+// instead of the fp16 bias / GELU / residual epilogue -- the Hessian accumulation of the GPTQ solver
+// (samq_syrk_f32_fwd below); bias / residual / rowmap are ignored.
+template <int BM, bool FUSED, bool GELU, int BITS = 4, bool F32ACC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                const __half* __restrict__ bias, const __half* residual, __half* y, int M, int N,
-               int K, int groupsize, const RowMap rowmap) {
+               int K, int groupsize, const RowMap rowmap, float alpha, float beta) {
   using C = Cfg<BM, FUSED, BITS>;
   constexpr int kWStageBytes = C::kWStageBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -98,8 +101,8 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_kb = K / kBK;
-  const int NT = N / kBN;
+  const int num_kb = (K + kBK - 1) / kBK;   // a ragged last k-block is zero-filled by TMA (dense mode)
+  const int NT = (N + kBN - 1) / kBN;       // ragged only for the fp32 Hessian kernel (rows beyond N: TMA zero fill)
   const int MT = (M + BM - 1) / BM;
   const int num_tiles = NT * MT;
   // k-blocks this CTA walks through, over all of its tiles (tile i of this CTA is
@@ -252,6 +255,28 @@ qlinear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < BM / 32; ++c) {
         const int m0 = m_tile * BM + c * 32;
+        if constexpr (F32ACC) {
+          // lanes own n (consecutive), registers own m: every register is one coalesced 128-byte row segment
+          uint32_t r[32];
+          tmem_ld_x32(d_tmem + c * 32, r);
+          tmem_ld_wait();
+          if (c == BM / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          }
+          float* y32 = reinterpret_cast<float*>(y);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = m0 + j;
+            if (m < M && n < N) {
+              float* dst = y32 + static_cast<size_t>(m) * N + n;
+              const float v = alpha * __uint_as_float(r[j]);
+              *dst = beta != 0.f ? fmaf(beta, *dst, v) : v;
+            }
+          }
+          continue;
+        }
         EpiBlock<GELU> blk;
         blk.prefetch(m0, M, N, n_tile * kBN + e * 32, lane, residual, rowmap);
         uint32_t r[32];
@@ -296,7 +321,7 @@ int launch_qlinear(const void* x, const void* w, const __half* scales, const int
   const int64_t tiles = NT * MT;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(*mx, *mw, scales, qzeros, bias, residual, y,
-                                              static_cast<int>(M), N, K, groupsize, rowmap);
+                                              static_cast<int>(M), N, K, groupsize, rowmap, 1.f, 0.f);
   count_launch();
   return check_launch("qlinear_kernel");
 }
@@ -408,6 +433,37 @@ extern "C" int samq_dense_linear_fwd(const void* x, const void* wt, const void* 
   return launch_dense(x, wt, reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(residual),
                       reinterpret_cast<__half*>(y), M, K, N, epilogue, identity,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Hessian accumulation of the GPTQ solver on the tensor cores: H = beta H + alpha At Bt^T
+extern "C" int samq_syrk_f32_fwd(const void* at, const void* bt, void* h, int n_feat, int64_t tokens, float alpha,
+                                 float beta, void* stream) {
+  using namespace samq;
+  const void* xt = at;
+  SAMQ_REQUIRE(at && bt && h, SAMQ_ERR_BAD_ARG, "samq_syrk_f32_fwd: null pointer");
+  SAMQ_REQUIRE(n_feat > 0 && n_feat <= 65536, SAMQ_ERR_BAD_SHAPE, "samq_syrk_f32_fwd: n_feat=%d out of range", n_feat);
+  SAMQ_REQUIRE(tokens > 0 && tokens % kBK == 0 && tokens < (1ll << 30), SAMQ_ERR_BAD_SHAPE,
+               "samq_syrk_f32_fwd: tokens=%lld must be a positive multiple of %d (pad with zero columns)",
+               (long long)tokens, kBK);
+  SAMQ_REQUIRE(reinterpret_cast<uintptr_t>(at) % 16 == 0 && reinterpret_cast<uintptr_t>(bt) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(h) % 16 == 0,
+               SAMQ_ERR_BAD_ARG, "samq_syrk_f32_fwd: pointers must be 16-byte aligned");
+  constexpr int BM = 192;
+  using C = Cfg<BM, false>;
+  const int K = static_cast<int>(tokens);
+  const CUtensorMap* mx = get_tensor_map_2d(xt, n_feat, K, static_cast<uint64_t>(K) * 2, BM, kBK, 2, 3);
+  const CUtensorMap* mw = get_tensor_map_2d(bt, n_feat, K, static_cast<uint64_t>(K) * 2, kBN, kBK, 2, 3);
+  if (!mx || !mw) return SAMQ_ERR_LAUNCH;
+  auto kern = qlinear_kernel<BM, false, false, 4, true>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes, "syrk"); rc != SAMQ_OK) return rc;
+  const int64_t tiles = static_cast<int64_t>((n_feat + kBN - 1) / kBN) * ((n_feat + BM - 1) / BM);
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  const RowMap identity = {0, 0, 0, 0, 0, 0};
+  kern<<<grid, kThreads, C::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+      *mx, *mw, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<__half*>(h), n_feat, n_feat, K, K, identity,
+      alpha, beta);
+  count_launch();
+  return check_launch("qlinear_kernel<syrk>");
 }
 
 extern "C" int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzeros,

@@ -85,6 +85,56 @@ def _check_packed(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, 
         assert t.device == x.device, f"{name} is on {t.device}, x on {x.device}"
 
 
+def hessian_accumulate(H: torch.Tensor, x: torch.Tensor, alpha: float, beta: float) -> None:
+    """``H = beta H + alpha x^T x`` in place for the GPTQ solver (``GPTQ.add_batch``): ``H`` fp32
+    ``[C, C]``, ``x`` ``[tokens, C]`` fp16 or fp32, on the tensor cores (``samq_syrk_f32_fwd``).
+    fp32 ``x`` is split as ``hi + 2^-11 lo`` with fp16 ``hi, lo`` and accumulated as
+    ``hi hi^T + 2^-11 (hi lo^T + lo hi^T)`` -- the dropped ``lo lo^T`` term is 2^-22 relative."""
+    _lib.require_cuda(x, "x")
+    assert H.dtype == torch.float32 and H.is_contiguous() and H.dim() == 2 and H.shape[0] == H.shape[1]
+    C = H.shape[0]
+    assert x.dim() == 2 and x.shape[1] == C and H.device == x.device
+    tokens = x.shape[0]
+    pad = (tokens + 63) // 64 * 64
+    lib = _lib.load()
+    with _dev_ctx(x):
+        def transposed(v):          # [C, pad] fp16, zero columns beyond `tokens`
+            t = torch.zeros((C, pad), dtype=torch.float16, device=x.device)
+            t[:, :tokens] = v.t()
+            return t
+        st = _lib.stream_ptr(x.device)
+        if x.dtype == torch.float16:
+            xt = transposed(x)
+            _lib.check(lib.samq_syrk_f32_fwd(_lib.ptr(xt), _lib.ptr(xt), _lib.ptr(H), C, pad, alpha, beta, st))
+            return
+        xf = x.float()
+        hi = xf.half()
+        lo = ((xf - hi.float()) * 2048.0).half()
+        hit, lot = transposed(hi), transposed(lo)
+        _lib.check(lib.samq_syrk_f32_fwd(_lib.ptr(hit), _lib.ptr(hit), _lib.ptr(H), C, pad, alpha, beta, st))
+        _lib.check(lib.samq_syrk_f32_fwd(_lib.ptr(hit), _lib.ptr(lot), _lib.ptr(H), C, pad, alpha / 2048.0, 1.0, st))
+        _lib.check(lib.samq_syrk_f32_fwd(_lib.ptr(lot), _lib.ptr(hit), _lib.ptr(H), C, pad, alpha / 2048.0, 1.0, st))
+
+
+def gptq_block(W: torch.Tensor, col0: int, ncols: int, U: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor,
+               colmap: torch.Tensor, maxq: int, Q: torch.Tensor, loss: torch.Tensor) -> torch.Tensor:
+    """One column block of the GPTQ rounding loop on the device (``samq_gptq_block_fwd``); returns the
+    scaled errors ``E[rows, ncols]`` that the caller propagates to the later blocks."""
+    _lib.require_cuda(W, "W")
+    for t in (W, U, scale, zero, Q, loss):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.device == W.device
+    assert colmap.dtype == torch.int32 and colmap.numel() == ncols and colmap.device == W.device
+    rows, ldw = W.shape
+    assert scale.shape == zero.shape and scale.shape[0] == rows and Q.shape == W.shape
+    with _dev_ctx(W):
+        E = torch.empty((rows, ncols), dtype=torch.float32, device=W.device)
+        _lib.check(_lib.load().samq_gptq_block_fwd(
+            _lib.ptr(W), ldw, rows, col0, ncols, _lib.ptr(U), U.shape[1], _lib.ptr(scale), _lib.ptr(zero),
+            scale.shape[1], _lib.ptr(colmap), int(maxq), _lib.ptr(Q), Q.shape[1], _lib.ptr(E), _lib.ptr(loss),
+            _lib.stream_ptr(W.device)))
+    return E
+
+
 def gather_cols(x: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     """``x[..., perm]`` for fp16 ``x[..., K]`` and an int32 permutation of ``K`` entries
     (act-order layers on the fused GEMM path, see ``QuantLinear.sorted_pack``)."""
