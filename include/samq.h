@@ -96,6 +96,29 @@ int samq_unpack_dequant(const int32_t* qweight, const int32_t* qzeros,
                         int K, int N, int bits, int groupsize, int transposed,
                         void* stream);
 
+/* Mask decoder, prompt side ----------------------------------
+ * Attention of the two-way transformer, replaces Attention.forward's
+ * `softmax(q k^T / sqrt(c_per_head)) v` (segment_anything/modeling/transformer.py:
+ * 225-238) between the prompt tokens and the image tokens, either direction:
+ *   out[b, i, h*hd:(h+1)*hd] = sum_j softmax_j(scale q[b,i,h].k[b,j,h]) v[b,j,h]
+ * q, out fp16 [B, Nq, heads*hd]; k, v fp16 [B, Nk, heads*hd]; hd in {16, 32, 64};
+ * fp32 softmax and accumulation. */
+int samq_attn_small_fwd(const void* q, const void* k, const void* v, void* out, int B, int heads,
+                        int Nq, int Nk, int hd, float scale, void* stream);
+
+/* Skinny linear for the decoder's prompt tokens and heads (nn.Linear on a few rows:
+ * transformer.py:151-153 MLPBlock, mask_decoder.py:155-178 MLP, the q/k/v/out
+ * projections of the token side):  y = act(x w^T + bias) + residual, x fp16 [M, K],
+ * w fp16 [N, K], bias fp16 [N] or NULL, residual fp16 [M, N] or NULL (fp16 add after the
+ * rounding, like the reference's `queries + mlp_out`), act 0 none / 1 exact-erf GELU /
+ * 2 ReLU; any N, K % 8 == 0.  The decoder's 4096-token linears use samq_dense_linear_fwd. */
+int samq_small_linear_fwd(const void* x, const void* w, const void* bias, const void* residual,
+                          void* y, int64_t M, int N, int K, int act, void* stream);
+
+/* Elementwise exact-erf GELU on fp16 (nn.GELU after the LayerNorm2d of
+ * MaskDecoder.output_upscaling, mask_decoder.py:55-59); n even; y may alias x. */
+int samq_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
+
 /* GPTQ calibration (offline solver) ---------------------------
  * Hessian accumulation, replaces GPTQ.add_batch (gptq.py:29-60: `self.H *= n/(n+1);
  * inp = sqrt(2/(n+1)) inp.float(); self.H += inp.matmul(inp.t())`) on the tensor cores:
@@ -136,7 +159,7 @@ int samq_gather_cols_fwd(const void* x, const int32_t* perm, void* y, int64_t M,
  * x, y, residual fp16 row-major; bias fp16 [N] or NULL; residual NULL or [M,N]
  * (may alias y).  fp32 accumulation on tcgen05 tensor cores.
  * bits 2/3/4/8 with g_idx == NULL and groupsize % 64 == 0 run the fused
- * unpack-in-registers->TMEM->tcgen05 kernel when M < 12288 or workspace == NULL; for
+ * unpack-in-registers->TMEM->tcgen05 kernel when M < 2048 or workspace == NULL; for
  * longer M (where re-dequantising the weight tile for every 192-token tile costs more
  * than reading fp16 weights from L2) and whenever g_idx != NULL it runs unpack_dequant
  * into `workspace` (K*N fp16 device scratch, may be reused between calls on the same

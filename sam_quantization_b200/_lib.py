@@ -42,6 +42,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     ),
+    "samq_attn_small_fwd": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "samq_small_linear_fwd": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "samq_gelu_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "samq_syrk_f32_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_void_p]),
     "samq_gptq_block_fwd": (
         c_int,

@@ -389,7 +389,11 @@ int qlinear_impl(const char* who, const void* x, const int32_t* qweight, const i
     //   fused 2-CTA  (SAMQ_GEMM=2cta, `make ABLATIONS=1` builds only, int4): cta_group::2 pair kernel, qlinear2.cu.
     // SAMQ_GEMM = fused | dense forces one of the product paths (tests: both must be bit-identical);
     // resolved once at load (Config, common.cuh), not per call.
-    constexpr int64_t kTwoKernelMinM = 12288;
+    // Threshold measured on the B200 (round 2): the SAM encoder at batch 1 (every GEMM M = 4096) runs
+    // 107.7 images/s on the fused kernel and 135.3 on unpack-once + pair GEMM; batch 2: 128.6 vs
+    // 157.8; the fused kernel wins where the pair kernel's 256x256 tiles cannot fill the GPU
+    // (M = 196: 21 vs 33 us per call).
+    constexpr int64_t kTwoKernelMinM = 2048;
     const int variant = config().gemm;
     const bool force_fused = variant == 1, force_dense = variant == 2;
 #ifdef SAMQ_ABLATIONS

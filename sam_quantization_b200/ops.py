@@ -15,7 +15,7 @@ from . import _lib
 
 
 #: M from which samq_qlinear_fwd switches int4 from the fused kernel to unpack-once + dense GEMM
-TWO_KERNEL_MIN_M = 12288
+TWO_KERNEL_MIN_M = 2048   # keep in sync with kTwoKernelMinM in csrc/qlinear.cu
 
 
 def _dev_ctx(t: torch.Tensor):
@@ -83,6 +83,64 @@ def _check_packed(x: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, 
         tensors.append(("bias", bias))
     for name, t in tensors:
         assert t.device == x.device, f"{name} is on {t.device}, x on {x.device}"
+
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def small_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(x @ weight.T + bias) + residual`` for a few rows (mask-decoder prompt tokens and heads):
+    ``x[..., K]`` fp16, ``weight[N, K]`` fp16 (``nn.Linear`` layout) -> ``[..., N]`` fp16."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x"); _check_half(weight, "weight")
+    N, K = weight.shape
+    assert x.shape[-1] == K and K % 8 == 0 and weight.device == x.device
+    M = x.numel() // K
+    if bias is not None:
+        _check_half(bias, "bias")
+        assert bias.numel() == N and bias.device == x.device
+    if residual is not None:
+        _check_half(residual, "residual")
+        assert residual.numel() == M * N and residual.device == x.device
+    with _dev_ctx(x):
+        y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float16, device=x.device)
+        if M == 0:
+            return y
+        _lib.check(_lib.load().samq_small_linear_fwd(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(residual),
+                                                     _lib.ptr(y), M, N, K, act, _lib.stream_ptr(x.device)))
+    return y
+
+
+def gelu(x: torch.Tensor) -> torch.Tensor:
+    """Exact-erf GELU, elementwise, fp16."""
+    _lib.require_cuda(x, "x")
+    _check_half(x, "x")
+    assert x.numel() % 2 == 0
+    with _dev_ctx(x):
+        y = torch.empty_like(x)
+        if x.numel():
+            _lib.check(_lib.load().samq_gelu_fwd(_lib.ptr(x), _lib.ptr(y), x.numel(), _lib.stream_ptr(x.device)))
+    return y
+
+
+def attn_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """``softmax(q k^T / sqrt(hd)) v`` per head without positional bias: ``q[B, Nq, C]``,
+    ``k, v[B, Nk, C]`` fp16, ``C = heads * hd`` with ``hd`` in {16, 32, 64} (transformer.py:225-238)."""
+    _lib.require_cuda(q, "q")
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _check_half(t, n)
+    B, Nq, C = q.shape
+    Nk = k.shape[1]
+    assert k.shape == v.shape == (B, Nk, C) and C % heads == 0 and k.device == q.device == v.device
+    hd = C // heads
+    if hd not in (16, 32, 64):
+        raise NotImplementedError(f"head dim {hd}: the decoder kernel serves 16, 32 and 64")
+    with _dev_ctx(q):
+        out = torch.empty_like(q)
+        _lib.check(_lib.load().samq_attn_small_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), B, heads, Nq,
+                                                   Nk, hd, 1.0 / math.sqrt(hd), _lib.stream_ptr(q.device)))
+    return out
 
 
 def hessian_accumulate(H: torch.Tensor, x: torch.Tensor, alpha: float, beta: float) -> None:

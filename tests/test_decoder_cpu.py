@@ -1,0 +1,103 @@
+"""Prompt encoder + mask decoder + click loop on the host: the torch path of this
+package's modules against the REFERENCE's own modules' outputs (tests/golden/decoder.npz, written by
+tests/golden/make_decoder_fixture.py, which also proves the state-dict contract with strict=True)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_decoder_fixture as mk  # noqa: E402  (weights from the seed, inputs; no reference import at module level)
+
+from sam_quantization_b200 import sam as S  # noqa: E402
+
+CASES = {"points": (True, False, False, True), "points_mask": (True, False, True, False),
+         "boxes": (False, True, False, True), "points_boxes": (True, True, False, False)}
+
+
+def run_case(pe, md, name, device="cpu", dtype=torch.float32):
+    use_pts, use_box, use_mask, multi = CASES[name]
+    emb, pts, labs, boxes, mask = (torch.from_numpy(a).to(device) for a in mk.inputs())
+    sparse, dense = pe(points=(pts.to(dtype), labs.to(dtype)) if use_pts else None,
+                       boxes=boxes.to(dtype) if use_box else None, masks=mask.to(dtype) if use_mask else None)
+    masks, iou = md(image_embeddings=emb.to(dtype), image_pe=pe.get_dense_pe().to(dtype),
+                    sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense, multimask_output=multi)
+    return sparse, dense, masks, iou
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_path_equals_the_reference_modules(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "decoder.npz"))
+    pe, md = mk.build_ours()
+    with torch.no_grad():
+        sparse, dense, masks, iou = run_case(pe, md, name)
+        assert np.allclose(pe.get_dense_pe()[:, ::8, ::4, ::4].numpy(), g["dense_pe_sub"], atol=1e-5)
+    sparse, dense, masks, iou = (t.detach() for t in (sparse, dense, masks, iou))
+    assert np.allclose(sparse.numpy(), g[f"{name}_sparse"], atol=1e-5)
+    assert np.allclose(dense[:, ::8, ::4, ::4].numpy(), g[f"{name}_dense_sub"], atol=1e-5)
+    assert masks.shape[1] == (3 if CASES[name][3] else 1)
+    assert np.abs(masks[:, :, ::4, ::4].numpy() - g[f"{name}_masks_sub"]).max() <= 1e-4 * float(g[f"{name}_masks_absmax"])
+    assert np.allclose(iou.numpy(), g[f"{name}_iou"], atol=1e-5)
+
+
+def test_iou_and_click_simulation():
+    gt = torch.zeros(2, 1, 32, 32)
+    gt[0, 0, 8:24, 8:24] = 1
+    gt[1, 0, 4:10, 4:10] = 1
+    gt[1, 0, 0, :] = -1                                            # ignored row
+    pred = torch.zeros(2, 1, 32, 32, dtype=torch.bool)
+    pred[0, 0, 8:24, 8:16] = True                                  # half of the object
+    pred[1, 0, 0:10, 4:10] = True                                  # object + false positives (one row ignored)
+    assert abs(float(S.get_iou(gt[0], pred[0])) - 0.5) < 1e-6
+    assert abs(float(S.get_iou(gt[1], pred[1])) - 36 / (36 + 18)) < 1e-6
+    rng = np.random.default_rng(0)
+    logits = torch.where(pred, 1.0, -1.0)
+    for _ in range(20):
+        pts, labs = S.next_clicks(logits, gt, rng)
+        assert pts.shape == (2, 1, 2) and labs.shape == (2, 1)
+        x0, y0 = (int(v) for v in pts[0, 0])
+        assert labs[0, 0] == 1 and gt[0, 0, y0, x0] == 1 and not pred[0, 0, y0, x0]     # missed pixel -> positive
+        x1, y1 = (int(v) for v in pts[1, 0])
+        assert labs[1, 0] == 0 and pred[1, 0, y1, x1] and gt[1, 0, y1, x1] != 1          # false positive -> negative
+    # no error left: a positive click on the object
+    perfect = torch.where(gt > 0, 1.0, -1.0)
+    pts, labs = S.next_clicks(perfect, gt, rng)
+    assert bool((labs == 1).all())
+
+
+def test_interactive_eval_loop_runs_the_reference_protocol():
+    """5 clicks, previous low-res mask fed back from the second click on, IoU per click; on random
+    weights the value itself means nothing -- shapes, prompt growth and determinism are checked."""
+    pe, md = mk.build_ours()
+    sam = S.Sam(torch.nn.Module(), pe, md)
+    sam.image_encoder.register_parameter("dummy", torch.nn.Parameter(torch.zeros(1)))
+    emb = torch.from_numpy(mk.inputs()[0])
+    gt = torch.zeros(1, 1, 1024, 1024)
+    gt[0, 0, 300:700, 200:800] = 1
+    seen = []
+    orig = md.forward
+
+    def spy(**kw):
+        seen.append((kw["sparse_prompt_embeddings"].shape[1], kw["dense_prompt_embeddings"].shape))
+        return orig(**kw)
+
+    md.forward = lambda image_embeddings, image_pe, sparse, dense, multi: spy(
+        image_embeddings=image_embeddings, image_pe=image_pe, sparse_prompt_embeddings=sparse,
+        dense_prompt_embeddings=dense, multimask_output=multi)
+    r1 = S.interactive_eval(sam, torch.zeros(1, 3, 1024, 1024), gt, num_clicks=5, seed=3, image_embeddings=emb)
+    assert r1["iou_per_click"].shape == (5, 1) and r1["low_res_logits"].shape == (1, 1, 256, 256)
+    assert [s[0] for s in seen] == [2, 3, 4, 5, 6]                 # clicks so far + the "not a point" pad
+    r2 = S.interactive_eval(sam, torch.zeros(1, 3, 1024, 1024), gt, num_clicks=5, seed=3, image_embeddings=emb)
+    assert torch.equal(r1["iou_per_click"], r2["iou_per_click"])
+
+
+def test_build_sam_module_tree():
+    sam = S.build_sam("vit_b", depth=1, global_attn_indexes=())
+    keys = set(sam.state_dict())
+    for k in ("image_encoder.pos_embed", "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix",
+              "prompt_encoder.mask_downscaling.6.weight", "mask_decoder.transformer.layers.1.cross_attn_image_to_token.out_proj.bias",
+              "mask_decoder.output_hypernetworks_mlps.3.layers.2.weight", "mask_decoder.iou_prediction_head.layers.0.weight",
+              "mask_decoder.output_upscaling.3.weight", "mask_decoder.transformer.norm_final_attn.weight"):
+        assert k in keys, k

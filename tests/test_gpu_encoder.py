@@ -100,7 +100,7 @@ def test_pad_skipping_block_is_bit_identical(cuda_device, tmp_path, samq_env, ba
     store -> attention that un-partitions in its store -> plain proj GEMM) never multiplies the
     zero-padding tokens of the 70x70 window layout; SAMQ_PAD_SKIP=0 is the reference's order of
     operations (partition, multiply everything, drop).  Same dot products -> identical bits.
-    batch 4 takes the unpack-once + CTA-pair GEMM path (M >= 12288), batch 1 the fused kernel."""
+    Both batches take the unpack-once + CTA-pair GEMM path by default (M >= 2048)."""
     samq_env.unset("SAMQ_ATTN_WIN")   # both forms on the default windowed kernel
     cfg = dict(embed_dim=640, depth=2, num_heads=8, global_attn_indexes=(1,))
     enc, _ = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=8, device=cuda_device)
@@ -243,7 +243,7 @@ def test_vith_width_blocks_at_the_benchmarked_batch(cuda_device, golden_dir, tmp
     """The benchmark's shapes: width 1280, 16 heads of 80, batch 32 (M = 131072 GEMM rows, 800
     windows, 32 global images), two blocks.  The oracle checks three images of the batch (CPU time);
     the rest is covered by the size-independent property that no op crosses the batch: a slice of
-    four images run alone (same kernel path: M >= 12288) gives identical bits."""
+    four images run alone (same kernel path) gives identical bits."""
     g, enc, state = _vith_d2_q4(golden_dir, tmp_path, cuda_device)
     x = torch.from_numpy(synth.tokens_input(32, 64, 1280, seed=11)).half()
     ref_state = oe.dequant_state(state, 4, 128)

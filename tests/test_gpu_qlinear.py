@@ -155,7 +155,7 @@ def test_cta_pair_kernel_equals_single_cta_kernel(cuda_device, samq_env, K, N, M
 
 @pytest.mark.parametrize("K,N,gs", [(1280, 1280, 128), (320, 256, 64), (64, 512, 64), (192, 256, 64)])
 def test_size_dispatch_two_kernel_path_equals_fused(cuda_device, samq_env, K, N, gs):
-    """M >= 12288 takes unpack-once + dense GEMM; it must equal the fused kernel bit for bit.
+    """M >= 2048 takes unpack-once + dense GEMM; it must equal the fused kernel bit for bit.
     K = 320, 64, 192: short reductions (fewer k-blocks than pipeline stages, odd counts)."""
     M = 12288 + 77
     qw, qz, sc, _ = rand_packed(K, N, 4, gs, seed=13)
