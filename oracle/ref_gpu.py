@@ -191,7 +191,7 @@ def time_loop(fn, iters=20, warm=5):
 @section("microbench")
 def run_microbench(dev, peaks):
     import gptq_triton.quant_linear as rql
-    from sam_quantization_b200 import ops
+    from sam_quantization_b200 import _lib, ops
 
     rql.workspace = torch.empty(32768 * 5120, dtype=torch.float16, device=dev)   # SURVEY trap 6
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -229,6 +229,16 @@ def run_microbench(dev, peaks):
                     if bits == 4:
                         t = time_loop(lambda: ops.qlinear(x, qwb, qzb, sc, bits, 128, bias))
                         rec["ours_int4_bias_loop_us"] = round(t, 2)
+                    # both product paths forced, to document the dispatch rule (default: fused below
+                    # M = 2048, unpack-once + pair GEMM from there on)
+                    for variant in ("fused", "dense"):
+                        os.environ["SAMQ_GEMM"] = variant
+                        _lib.reload_config()
+                        t = time_cold(lambda: ops.qlinear(x, qwb, qzb, sc, bits, 128, bias), flush)
+                        rec[f"ours_int{bits}_{variant}_us"] = round(t, 2)
+                        rec[f"ours_int{bits}_{variant}_tflops"] = tf(t)
+                    os.environ.pop("SAMQ_GEMM", None)
+                    _lib.reload_config()
                 # same result? (ours vs the reference kernel, identical packed int4 buffers)
                 y_ref = rql.triton_matmul4(128, x, qw, sc, qz, bias).float()
                 y = ops.qlinear(x, qw, qz, sc, 4, 128, bias).float()

@@ -1,7 +1,10 @@
 // Developer microbenchmark: wait-time breakdown of the global attention kernel.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DSAMQ_ATTN_PROFILE --expt-relaxed-constexpr \
 //        -I include tests/micro/attn_prof.cu sam_quantization_b200/csrc/runtime.cu -o tests/micro/attn_prof -lcuda
+// (one translation unit on purpose: the profile counters live in an anonymous namespace)
 #include "../../sam_quantization_b200/csrc/attention.cu"
+#include "../../sam_quantization_b200/csrc/attention_win.cu"
+#include "../../sam_quantization_b200/csrc/attention_glob.cu"
 #include <cstdio>
 #include <vector>
 int main(int argc, char** argv) {
