@@ -396,6 +396,27 @@ def main():
             acc[1] += dt
             acc[2] += fl
 
+    # optional final gather of the embeddings (launcher.ShardedEncoder(gather=True)): OUTSIDE the
+    # timed region and not part of `value`; timed here so that its NVLink cost is on record
+    gather_info = None
+    if world > 1:
+        bufs = [torch.empty_like(out) for _ in range(world)]
+        for _ in range(2):
+            dist.all_gather(bufs, out)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.all_gather(bufs, out)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / 5
+        nbytes = out.numel() * out.element_size()
+        gather_info = {"ms": gms, "bytes_per_rank": nbytes,
+                       "recv_GBps_per_rank": nbytes * (world - 1) / gms / 1e6,
+                       "note": "dist.all_gather (NCCL over NVLink) of every rank's [B, 256, 64, 64] fp16 embeddings; "
+                               "optional, after the step, not inside the timed region"}
+        del bufs
     t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     per_rank = [t_ms.clone() for _ in range(world)]
     if world > 1:
@@ -424,6 +445,7 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "launch": "eager" if args.no_graph else "cuda-graph replay of the whole encoder forward",
             "per_rank_ms_per_step": [round(float(t[0]) / args.steps, 3) for t in per_rank],
+            "final_allgather": gather_info,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 1024 * 1024 * 2,
                     "d2h_bytes_per_step": B * 256 * 64 * 64 * 2,
                     "api": ("eager forward on host tensors (serial H2D, encoder, D2H)" if args.no_graph else
