@@ -45,15 +45,27 @@ class QuantAttention(nn.Module):
         self.use_rel_pos = use_rel_pos
         self.relw_mode = relw_mode
 
-    def attention(self, qkv: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
-        """softmax(scale q k^T + rel-pos bias) v on the packed qkv GEMM output."""
+    def _tables(self, kh: int, kw: int):
+        """fp16 rel-pos tables of exactly 2*kh-1 / 2*kw-1 rows for the kernels: the parameters
+        themselves in SAM's own case, linearly interpolated (image_encoder.py:348-358) when the
+        checkpoint was trained at another grid size; cached per parameter version."""
         if not self.use_rel_pos:
             raise NotImplementedError          # fused_attention.py:134-135
-        rph, rpw = self.rel_pos_h, self.rel_pos_w
-        if rph.dtype != torch.float16:
-            rph, rpw = rph.half(), rpw.half()
-        return ops.attn_relpos(qkv, rph.contiguous(), rpw.contiguous(), B, H, W, self.num_heads,
-                               self.scale, _RELW[self.relw_mode])
+        key = (kh, kw, self.rel_pos_h.data_ptr(), self.rel_pos_h._version, self.rel_pos_w.data_ptr(),
+               self.rel_pos_w._version, self.rel_pos_h.dtype)
+        hit = getattr(self, "_table_cache", None)
+        if hit is None or hit[0] != key:
+            from .image_encoder import resize_rel_pos
+
+            rph = resize_rel_pos(self.rel_pos_h.detach(), 2 * kh - 1).half().contiguous()
+            rpw = resize_rel_pos(self.rel_pos_w.detach(), 2 * kw - 1).half().contiguous()
+            hit = self._table_cache = (key, rph, rpw)
+        return hit[1], hit[2]
+
+    def attention(self, qkv: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+        """softmax(scale q k^T + rel-pos bias) v on the packed qkv GEMM output."""
+        rph, rpw = self._tables(H, W)
+        return ops.attn_relpos(qkv, rph, rpw, B, H, W, self.num_heads, self.scale, _RELW[self.relw_mode])
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None,
                 unpartition_window: int = 0, partition_window: int = 0) -> torch.Tensor:
@@ -69,13 +81,9 @@ class QuantAttention(nn.Module):
         if partition_window:
             ws = partition_window
             B, H, W, _ = x.shape
+            rph, rpw = self._tables(ws, ws)
             qkv = self.qkv_proj.forward_partition(x, ws)
-            if not self.use_rel_pos:
-                raise NotImplementedError      # fused_attention.py:134-135
-            rph, rpw = self.rel_pos_h, self.rel_pos_w
-            if rph.dtype != torch.float16:
-                rph, rpw = rph.half(), rpw.half()
-            o = ops.attn_relpos_unpartition(qkv, rph.contiguous(), rpw.contiguous(), B, H, W, ws, self.num_heads,
+            o = ops.attn_relpos_unpartition(qkv, rph, rpw, B, H, W, ws, self.num_heads,
                                             self.scale, _RELW[self.relw_mode])
             return self.o_proj(o, residual=residual) if residual is not None else self.o_proj(o)
         B, H, W, _ = x.shape

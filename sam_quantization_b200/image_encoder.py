@@ -131,14 +131,26 @@ def window_unpartition(windows: torch.Tensor, window_size: int, pad_hw: Tuple[in
     return x
 
 
+def resize_rel_pos(rel_pos: torch.Tensor, length: int) -> torch.Tensor:
+    """Rel-pos table ``[L, C]`` linearly interpolated to ``length`` rows when ``L != length``
+    (image_encoder.py:348-358: a checkpoint trained at another grid size); identity otherwise."""
+    if rel_pos.shape[0] == length:
+        return rel_pos
+    t = F.interpolate(rel_pos.float().reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1), size=length, mode="linear")
+    return t.reshape(-1, length).permute(1, 0).to(rel_pos.dtype)
+
+
 def get_rel_pos(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tensor:
-    """R[i, j, :] = rel_pos[i - j + (k_size - 1)] for the square, non-interpolated case
-    SAM uses (image_encoder.py:336-366: table length is 2*size-1, :246-247)."""
-    if q_size != k_size or rel_pos.shape[0] != 2 * q_size - 1:
-        raise NotImplementedError("only square windows with a 2*size-1 table (SAM's case)")
-    idx = torch.arange(q_size, device=rel_pos.device)[:, None] - \
-        torch.arange(k_size, device=rel_pos.device)[None, :] + (k_size - 1)
-    return rel_pos[idx]
+    """R[i, j, :] = table[i' - j' + (k_size - 1) * max(q_size / k_size, 1)] with the coordinates of
+    the shorter side stretched to the longer one and the table interpolated to
+    2 * max(q_size, k_size) - 1 rows when its length differs (image_encoder.py:336-366).  SAM's own
+    case is square with a table of exactly 2 * size - 1 rows: R[i, j] = rel_pos[i - j + size - 1]."""
+    table = resize_rel_pos(rel_pos, int(2 * max(q_size, k_size) - 1))
+    dev = rel_pos.device
+    q_coords = torch.arange(q_size, device=dev)[:, None] * max(k_size / q_size, 1.0)
+    k_coords = torch.arange(k_size, device=dev)[None, :] * max(q_size / k_size, 1.0)
+    idx = (q_coords - k_coords) + (k_size - 1) * max(q_size / k_size, 1.0)
+    return table[idx.long()]
 
 
 def decomposed_rel_pos(q: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor,
