@@ -12,7 +12,7 @@
 // k per int32 of qweight[k/f, n]; 32/bits consecutive n per int32 of
 // qzeros[g, n/f] storing zero-1.  3-bit (extension, quant.py:160-180): 32 values
 // form a 96-bit little-endian bit stream over 3 consecutive words.
-#include "common.cuh"
+#include "qlinear_common.cuh"
 
 namespace samq {
 
@@ -176,6 +176,87 @@ dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* _
   dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
+// ---- fast path for every format, transposed output Wt[N, K] (feeds the dense tcgen05 GEMM) -------
+// One lane = one output feature, one warp = 32 consecutive features x one k-block of 64: the packed
+// rows are read as 128 contiguous bytes per warp, unpacked in registers by the SAME code as the fused
+// GEMM (qlinear_common.cuh::unpack_kblock / unpack_q_h2: bit-identical by construction), and each
+// lane writes its 128 bytes of Wt.  GIDX: act-order groups -- scale and zero point are looked up per k
+// through g_idx (the k-block's 64 group ids are loaded once per warp and passed round by shuffle).
+// The generic kernel above needs ~35 us per ViT-H layer (one thread per 2 columns x 32 k, results
+// staged in local memory); this one is HBM / L2-bound.
+template <int BITS, bool GIDX>
+__global__ void __launch_bounds__(256)
+dequant_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                          const __half* __restrict__ scales, const int32_t* __restrict__ g_idx,
+                          __half* __restrict__ wt, int K, int N, int groupsize) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int kblocks = K >> 6;
+  const int nb = static_cast<int>(warp_global / kblocks), kb = static_cast<int>(warp_global - static_cast<int64_t>(nb) * kblocks);
+  const int n = nb * 32 + lane;
+  if (nb * 32 >= N) return;
+  // packed words of this feature's k-block: rows kb*2*BITS .. +2*BITS-1, column n
+  uint32_t q[2 * BITS];
+#pragma unroll
+  for (int r = 0; r < 2 * BITS; ++r)
+    q[r] = static_cast<uint32_t>(qweight[static_cast<int64_t>(kb * 2 * BITS + r) * N + n]);
+  // zero point of feature n in a qzeros row: word / shift depend on n only
+  constexpr int kFieldsPerWord = BITS == 3 ? 1 : 32 / BITS;
+  const int zwords = BITS == 3 ? N / 32 * 3 : N / kFieldsPerWord;
+  const int zbit = BITS == 3 ? 3 * (n & 31) : (n % kFieldsPerWord) * BITS;
+  const int zword = BITS == 3 ? (n >> 5) * 3 + (zbit >> 5) : n / kFieldsPerWord;
+  const int zshift = zbit & 31;
+  const bool zstraddle = BITS == 3 && zshift + 3 > 32;
+  auto zero_plus_one = [&](int g) {
+    const int32_t* zp = qzeros + static_cast<int64_t>(g) * zwords + zword;
+    uint32_t z = static_cast<uint32_t>(zp[0]) >> zshift;
+    if (BITS == 3 && zstraddle) z |= static_cast<uint32_t>(zp[1]) << (32 - zshift);
+    return (z & ((1u << BITS) - 1u)) + 1u;
+  };
+  uint32_t out[32];
+  if constexpr (!GIDX) {
+    const int g = (kb * 64) / groupsize;      // groupsize is a multiple of 64 here
+    const __half s = scales[static_cast<int64_t>(g) * N + n];
+    const __half zs = __hmul_rn(__uint2half_rn(zero_plus_one(g)), s);
+    unpack_kblock<BITS>(q, h2_dup(s), h2_dup(__hneg(zs)), out);
+  } else {
+    unpack_q_h2<BITS>(q, out);
+    const int g_lo = g_idx[kb * 64 + lane], g_hi = g_idx[kb * 64 + 32 + lane];
+#pragma unroll
+    for (int pr = 0; pr < 32; ++pr) {
+      uint32_t s2 = 0, nzs2 = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = 2 * pr + e;
+        const int g = __shfl_sync(0xffffffffu, k < 32 ? g_lo : g_hi, k & 31);
+        const __half s = scales[static_cast<int64_t>(g) * N + n];
+        const __half nzs = __hneg(__hmul_rn(__uint2half_rn(zero_plus_one(g)), s));
+        s2 |= static_cast<uint32_t>(__half_as_ushort(s)) << (16 * e);
+        nzs2 |= static_cast<uint32_t>(__half_as_ushort(nzs)) << (16 * e);
+      }
+      out[pr] = h2_fma(out[pr], s2, nzs2);
+    }
+  }
+  pdl_wait();   // the scratch Wt may still be read by an earlier GEMM
+  uint4* dst = reinterpret_cast<uint4*>(wt + static_cast<int64_t>(n) * K + kb * 64);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) dst[v] = make_uint4(out[4 * v], out[4 * v + 1], out[4 * v + 2], out[4 * v + 3]);
+}
+
+template <int BITS>
+static int launch_dequant_transposed(const int32_t* qweight, const int32_t* qzeros, const __half* scales,
+                                     const int32_t* g_idx, __half* wt, int K, int N, int groupsize, cudaStream_t st) {
+  const int64_t warps = static_cast<int64_t>(N / 32) * (K / 64);
+  const dim3 grid(static_cast<unsigned>((warps + 7) / 8)), block(256);
+  if (g_idx)
+    launch_pdl(1, dequant_transposed_kernel<BITS, true>, grid, block, 0, st, qweight, qzeros, scales, g_idx, wt, K, N, groupsize);
+  else
+    launch_pdl(1, dequant_transposed_kernel<BITS, false>, grid, block, 0, st, qweight, qzeros, scales, g_idx, wt, K, N, groupsize);
+  count_launch();
+  return check_launch("dequant_transposed_kernel");
+}
+
 template <int BITS>
 static int launch_unpack(const int32_t* qweight, const int32_t* qzeros, const __half* scales,
                          const int32_t* g_idx, __half* w_out, int K, int N, int groupsize,
@@ -211,6 +292,16 @@ int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* sc
     launch_pdl(1, dequant4_transposed_kernel, dim3((warps + 7) / 8), dim3(256), 0, st, qweight, qzeros, s, w, K, N, groupsize);
     count_launch();
     return check_launch("dequant4_transposed_kernel");
+  }
+  // every other format (and act-order int4) on the same lane-per-feature scheme; the generic kernel
+  // keeps the untransposed layout and the odd shapes
+  if (transposed && K % 64 == 0 && N % 32 == 0 && (g_idx != nullptr || groupsize % 64 == 0)) {
+    switch (bits) {
+      case 2: return launch_dequant_transposed<2>(qweight, qzeros, s, g_idx, w, K, N, groupsize, st);
+      case 3: return launch_dequant_transposed<3>(qweight, qzeros, s, g_idx, w, K, N, groupsize, st);
+      case 4: return launch_dequant_transposed<4>(qweight, qzeros, s, g_idx, w, K, N, groupsize, st);
+      default: return launch_dequant_transposed<8>(qweight, qzeros, s, g_idx, w, K, N, groupsize, st);
+    }
   }
   switch (bits) {
     case 2: return launch_unpack<2>(qweight, qzeros, s, g_idx, w, K, N, groupsize, transposed, st);

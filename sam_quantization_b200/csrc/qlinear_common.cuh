@@ -327,6 +327,60 @@ __device__ __forceinline__ void unpack_kblock(const uint32_t (&q)[2 * BITS], uin
   }
 }
 
+// The integer fields of one k-block (64 k) of one feature as EXACT fp16 pairs (q_k, q_k+1), before
+// scale / zero are applied: the first half of unpack_kblock, for callers whose scale differs per k
+// (act-order groups in the standalone unpack kernel, dequant.cu).
+template <int BITS>
+__device__ __forceinline__ void unpack_q_h2(const uint32_t (&q)[2 * BITS], uint32_t (&out)[32]) {
+  if constexpr (BITS == 4) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t w = q[r], w8 = w >> 8;
+      const uint32_t a = h2_add(nib_to_h2(w), 0xe400e400u), b = h2_add(nib_hi_to_h2(w), 0xd400d400u);
+      const uint32_t c = h2_add(nib_to_h2(w8), 0xe400e400u), d = h2_add(nib_hi_to_h2(w8), 0xd400d400u);
+      out[4 * r + 0] = prmt(a, b, 0x5410);
+      out[4 * r + 1] = prmt(c, d, 0x5410);
+      out[4 * r + 2] = prmt(a, b, 0x7632);
+      out[4 * r + 3] = prmt(c, d, 0x7632);
+    }
+  } else if constexpr (BITS == 8) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      out[2 * r + 0] = h2_add(prmt(q[r], 0x64646464u, 0x4140), 0xe400e400u);
+      out[2 * r + 1] = h2_add(prmt(q[r], 0x64646464u, 0x4342), 0xe400e400u);
+    }
+  } else if constexpr (BITS == 2) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = h2_add(lop3_and_or(q[r] >> (2 * j), 0x00030003u, 0x64006400u), 0xe400e400u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        out[8 * r + j] = prmt(h[2 * j], h[2 * j + 1], 0x5410);
+        out[8 * r + 4 + j] = prmt(h[2 * j], h[2 * j + 1], 0x7632);
+      }
+    }
+  } else {
+    static_assert(BITS == 3, "bits");
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int pr = 0; pr < 16; ++pr) {
+        uint32_t f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int bit = 3 * (2 * pr + e), word = bit >> 5, off = bit & 31;
+          uint32_t v = q[3 * c + word] >> off;
+          if (off + 3 > 32) v |= q[3 * c + word + 1] << (32 - off);
+          f[e] = v & 7u;
+        }
+        out[16 * c + pr] = h2_add((f[0] | (f[1] << 16)) | 0x64006400u, 0xe400e400u);
+      }
+    }
+  }
+}
+
 // One dequant warp's main loop (shared by the 1-CTA and 2-CTA kernels).
 //
 // `set` (0/1) takes the CTA-wide k-blocks kbc = set, set+2, ...  For each of them the warp
