@@ -216,9 +216,27 @@ def make_encoder_q4_fixture():
     print("encoder q4 fixture", y.shape, float(np.abs(y).max()))
 
 
+def make_relpos_fixture():
+    """Reference get_rel_pos (image_encoder.py:336-366) incl. its interpolation branch (:348-358): tables
+    whose length differs from 2 * max(q, k) - 1, and non-square q / k."""
+    from segment_anything.modeling.image_encoder import get_rel_pos
+
+    out = {}
+    cases = [(14, 14, 27), (14, 14, 127), (64, 64, 27), (7, 14, 27), (14, 7, 13), (10, 10, 33)]
+    for n, (q, k, L) in enumerate(cases):
+        t = torch.from_numpy(np.random.default_rng(40 + n).standard_normal((L, 8)).astype(np.float32))
+        out[f"c{n}_table"] = t.numpy()
+        out[f"c{n}_R"] = get_rel_pos(q, k, t).numpy()
+    np.savez_compressed(os.path.join(HERE, "rel_pos_interp.npz"), cases=np.array(cases), **out)
+    print("rel-pos fixture", len(cases))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder_q4":
         make_encoder_q4_fixture()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "relpos":
+        make_relpos_fixture()
         sys.exit(0)
     torch.manual_seed(0)
     make_pack_fixtures()
@@ -227,4 +245,5 @@ if __name__ == "__main__":
     make_partition_fixture()
     make_encoder_fixture()
     make_encoder_q4_fixture()
+    make_relpos_fixture()
     print("done")

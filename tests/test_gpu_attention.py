@@ -149,3 +149,27 @@ def test_unsupported_shapes_raise(cuda_device):
     rp = torch.zeros(63, 64, dtype=torch.float16, device=cuda_device)
     with pytest.raises(AssertionError):
         ops.attn_relpos(qkv, rp, rp, 1, 32, 32, 2, 0.1)
+
+
+def test_quant_attention_interpolates_rel_pos_tables_of_another_grid(cuda_device):
+    """A checkpoint trained at another grid size carries rel-pos tables that are not 2*size-1 rows
+    long; the reference resizes them linearly (image_encoder.py:348-358).  QuantAttention does the
+    same once per parameter version and hands the kernel the resized tables: result = the oracle's
+    attention with tables resized by the (reference-pinned) host get_rel_pos path."""
+    from sam_quantization_b200 import image_encoder as ie
+    from sam_quantization_b200.fused_attention import QuantAttention
+
+    heads, hd, E, B = 2, 64, 14, 3
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.empty(B, E * E, 3 * heads * hd).normal_(0.0, 0.5, generator=g).half()
+    rph = torch.empty(2 * 32 - 1, hd).normal_(0.0, 0.3, generator=g)          # trained for a 32 x 32 grid
+    rpw = torch.empty(2 * 32 - 1, hd).normal_(0.0, 0.3, generator=g)
+    attn = QuantAttention(None, None, heads, 0.5, True, torch.nn.Parameter(rph.to(cuda_device)),
+                          torch.nn.Parameter(rpw.to(cuda_device)))
+    out = attn.attention(qkv.to(cuda_device), B, E, E)
+    t1 = attn._tables(E, E)
+    assert t1[0].shape == (2 * E - 1, hd) and attn._tables(E, E)[0] is t1[0]                 # resized once, cached
+    ref = oe.attention_core(qkv, ie.resize_rel_pos(rph, 2 * E - 1).half(), ie.resize_rel_pos(rpw, 2 * E - 1).half(),
+                            B, E, E, heads, 0.5, "reference", round_tables=True)
+    err, mag, cos = report(out, ref)
+    assert err <= ATOL and cos >= 0.9999, (err, mag, cos)

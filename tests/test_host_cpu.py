@@ -242,3 +242,16 @@ def test_sorted_pack_of_an_act_order_layer_is_the_same_weight(bits):
     assert np.array_equal(np.sort(gi[perm.numpy()]), gi[perm.numpy()])   # groups contiguous and ascending
     layer.g_idx = torch.from_numpy(np.minimum(gi, 1))        # unequal group sizes: not sortable into gs-blocks
     assert layer.sorted_pack() is None
+
+
+def test_get_rel_pos_matches_reference_including_interpolation(golden_dir):
+    """image_encoder.py:336-366 with its interpolation branch (:348-358), against the reference
+    function's outputs (tests/golden/rel_pos_interp.npz)."""
+    g = np.load(os.path.join(golden_dir, "rel_pos_interp.npz"))
+    for n, (q, k, L) in enumerate(g["cases"]):
+        R = ie.get_rel_pos(int(q), int(k), torch.from_numpy(g[f"c{n}_table"]))
+        assert R.shape == g[f"c{n}_R"].shape
+        assert np.allclose(R.numpy(), g[f"c{n}_R"], atol=1e-6), (q, k, L)
+    # SAM's own case stays the plain gather
+    t = torch.arange(27, dtype=torch.float32)[:, None].repeat(1, 2)
+    assert torch.equal(ie.get_rel_pos(14, 14, t)[3, 5], t[3 - 5 + 13])
