@@ -73,7 +73,10 @@ attn_glob3_kernel(const __grid_constant__ CUtensorMap map_qkv_main, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  // images (and heads) from the END of the batch: the qkv GEMM wrote its output front to back, so the
+  // last images are what the L2 still holds, and the proj GEMM reads this kernel's output from the
+  // front, which is then written last (same reasoning as in attention_win.cu / layernorm.cu)
+  const int q_tile = blockIdx.x, head = gridDim.y - 1 - blockIdx.y, b = gridDim.z - 1 - blockIdx.z;
   const int D = heads * HD;
   const int m0 = q_tile * 128;
 

@@ -129,7 +129,8 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
         const int st = n & 1;
         const uint32_t ph = (n >> 1) & 1;
-        const int b = item / heads, head = item % heads;
+        const int ri = n_items - 1 - item;   // items from the end: see the note at the softmax warps
+        const int b = ri / heads, head = ri % heads;
         uint8_t* sQ = smem + C::oQ + st * C::kQStage;
         uint8_t* sKV = smem + C::oKV + st * C::kKVStage;
         mbar_wait(&q_empty[st], ph ^ 1);
@@ -257,7 +258,11 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const int st = n & 1;
       const uint32_t pn = n & 1;
-      const int b = item / heads, head = item % heads;
+      // (window, head) items are taken from the END of the qkv tensor: the qkv GEMM wrote it front to
+      // back, so its tail is what the L2 still holds; and the proj GEMM reads this kernel's output
+      // from the front, which is then written last
+      const int ri = n_items - 1 - item;
+      const int b = ri / heads, head = ri % heads;
       uint8_t* sQ = smem + C::oQ + st * C::kQStage;
 
       // ---- bias values out of TMEM: bh[k] = T_h[row][mh + 13 - k], bw[k] = T_w[row][rw + 13 - k],

@@ -216,7 +216,12 @@ layernorm_fast_kernel(const __half* __restrict__ x, const __half* __restrict__ g
                       int H, int W, int ws, int nH, int nW, float eps) {
   constexpr int C = NVEC * 256;
   const int lane = threadIdx.x & 31;
-  const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  // Rows are walked from the END of the tensor (block 0 takes the last rows).  The producer of x -- a
+  // GEMM epilogue -- wrote the tensor front to back, so its last ~100 MB are still in the 126 MB L2
+  // when this kernel starts; and the consumer of y (the next GEMM) starts at row 0, which this
+  // kernel then writes last.  A 335 MB activation does not fit in L2, its two ends do.
+  const int64_t blk = PARTITION ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(gridDim.x) - 1 - blockIdx.x;
+  const int64_t r0 = (blk * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
   const __half* src[2];
   bool live[2], pad[2];
 #pragma unroll
