@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--model", default="vit_h", choices=sorted(MODEL_NAMES))
     ap.add_argument("--batch", type=int, default=32,
                     help="images per GPU per step (BASELINE config 3 is a batch sweep: 8 / 16 / 32 / 64 per GPU give "
-                         "179 / 182 / 185 / 188 images/s on one B200)")
+                         "181 / 182 / 186 / 185 images/s on one B200)")
     ap.add_argument("--bits", type=int, default=4, choices=[2, 3, 4, 8],
                     help="weight bits (BASELINE config 4: 3 and 8 with --act-order)")
     ap.add_argument("--act-order", action="store_true", help="permutation-derived g_idx (non-contiguous groups)")
@@ -223,7 +223,9 @@ def main():
               "global_batch": args.batch * world, "parallelism": f"dp{world} (replicas, no data-path collective)",
               "l2": "no explicit flush: the working set of one step (packed weights + activations of the batch, "
                     ">1 GB already at batch 8) exceeds the 126 MB L2; input batches rotate over 3 buffers",
-              "batch_sweep_images_per_s_1gpu": {"8": 179, "16": 182, "32": 185, "64": 188}}
+              "batch_sweep_images_per_s_1gpu": {"1": 134, "8": 181, "16": 182, "32": 186, "64": 185,
+                                                "note": "round 2, one box (profiles/r02h_batch_sweep.txt; the same tree "
+                                                        "gave 198.5 at batch 32 on a faster box)"}}
 
     from sam_quantization_b200.synthetic import random_quantized_encoder
 
