@@ -54,7 +54,10 @@ typedef enum samq_relw_mode {
 
 /* Library / device ---------------------------------------------------------- */
 
-/* ABI version of this header (bumped on any signature change). */
+/* ABI version of this header (bumped on any signature change or new entry point).
+ * 1: round 1.  2: single-FMA dequant (the reference's Triton rounding), samq_config_reload /
+ * samq_has_ablations.  3: samq_gather_cols_fwd, samq_syrk_f32_fwd, samq_gptq_block_fwd,
+ * samq_attn_small_fwd, samq_small_linear_fwd, samq_gelu_fwd. */
 int samq_abi_version(void);
 
 /* Reason for the last non-OK status returned to the calling thread. */

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_strings():
     lib = _lib.load()
-    assert lib.samq_abi_version() == 2
+    assert lib.samq_abi_version() == 3
     assert lib.samq_has_ablations() == 0     # the shipped library holds the product kernels only
     # validation happens before any CUDA call, so these run on a GPU-less box
     rc = lib.samq_unpack_dequant(1, 1, 1, None, 1, 64, 64, 5, 64, 0, None)
