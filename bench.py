@@ -184,6 +184,30 @@ class CpuReference:
             return time.perf_counter() - t0
 
 
+def other_kernel_rooflines(other_ms, peaks, step_ms):
+    """Per kernel class: mean us per call, algorithmic GB/s and TFLOP/s, fraction of the roofline that
+    bounds it, share of the step (timed with CUDA events in the instrumented eager replay)."""
+    out = {}
+    for name, recs in other_ms.items():
+        if not recs:
+            continue
+        ms = sum(r[0] for r in recs)
+        gbps = sum(r[1] for r in recs) / ms / 1e6
+        tf = sum(r[2] for r in recs) / ms / 1e9
+        e = {"calls_per_step": len(recs) // 2, "us_per_call": round(ms / len(recs) * 1e3, 1),
+             "share_of_step": round(ms / 2 / step_ms, 4), "algorithmic_GBps": round(gbps, 1)}
+        if name == "attn_global":
+            e.update(bound="tensor / MUFU", TFLOPs=round(tf, 1), frac_of_burst_tensor_peak=round(tf / peaks["tflops"], 3),
+                     note="MUFU floor (16 ex2 / clk / SM) is 0.57 of the measured time at batch 32, DESIGN 5.2")
+        elif name == "attn_windowed":
+            e.update(bound="hbm", frac_of_hbm_peak=round(gbps / peaks["hbm_gbs"], 3), TFLOPs=round(tf, 1),
+                     frac_of_burst_tensor_peak=round(tf / peaks["tflops"], 3))
+        else:
+            e.update(bound="hbm", frac_of_hbm_peak=round(gbps / peaks["hbm_gbs"], 3))
+        out[name] = e
+    return out
+
+
 def packed_state_cpu(enc):
     """Reference-layout state (``...attn.qkv.qweight`` etc.) of a fused encoder, on the CPU."""
     out = {}
@@ -374,6 +398,44 @@ def main():
             rec.append((s, t, 2.0 * m * x.shape[-1] * qweight.shape[1], (m, x.shape[-1], qweight.shape[1])))
             return y
 
+        # the other kernel classes of the step, same method: LayerNorm (HBM-bound: 2 rows C 2 B), windowed
+        # attention (HBM-bound at this size: the qkv tensor in, the output out) and global attention
+        # (MUFU / tensor-bound: 4 S^2 hd per head + the in-kernel rel-pos products)
+        other = {"layernorm": [], "attn_windowed": [], "attn_global": []}
+        orig_ln, orig_aw, orig_ag = ops.layernorm, ops.attn_relpos_unpartition, ops.attn_relpos
+
+        def timed_ln(x, *a, **kw):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            y = orig_ln(x, *a, **kw)
+            t.record()
+            if x.shape[-1] >= 512:       # the block LayerNorms (the neck's 256-channel ones are noise)
+                other["layernorm"].append((s, t, 2.0 * x.numel() * 2, 0.0))
+            return y
+
+        def timed_aw(qkv, rph, rpw, Bq, H, W, ws, heads, *a, **kw):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            y = orig_aw(qkv, rph, rpw, Bq, H, W, ws, heads, *a, **kw)
+            t.record()
+            hd = qkv.shape[-1] // 3 // heads
+            nwin = qkv.numel() // qkv.shape[-1] // (ws * ws)
+            flops = nwin * heads * (4.0 * (ws * ws) ** 2 * hd + 4.0 * ws * ws * 2 * ws * hd)
+            other["attn_windowed"].append((s, t, (qkv.numel() + y.numel()) * 2.0, flops))
+            return y
+
+        def timed_ag(qkv, rph, rpw, Bq, H, W, heads, *a, **kw):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            y = orig_ag(qkv, rph, rpw, Bq, H, W, heads, *a, **kw)
+            t.record()
+            hd = qkv.shape[-1] // 3 // heads
+            S = H * W
+            flops = Bq * heads * (4.0 * S * S * hd + 4.0 * S * (H + W) * hd)
+            other["attn_global"].append((s, t, (qkv.numel() + y.numel()) * 2.0, flops))
+            return y
+
+        ops.layernorm, ops.attn_relpos_unpartition, ops.attn_relpos = timed_ln, timed_aw, timed_ag
         ops.qlinear = timed_qlinear
         ops.qlinear_unpartition = timed_unpartition
         ops.qlinear_partition = timed_partition
@@ -387,6 +449,8 @@ def main():
         ops.qlinear = orig
         ops.qlinear_unpartition = orig_unp
         ops.qlinear_partition = orig_part
+        ops.layernorm, ops.attn_relpos_unpartition, ops.attn_relpos = orig_ln, orig_aw, orig_ag
+        other_ms = {k: [(s.elapsed_time(t), by, fl) for s, t, by, fl in v] for k, v in other.items()}
         per_shape = {}
         for s, t, fl, shp in rec:
             dt = s.elapsed_time(t)
@@ -468,6 +532,7 @@ def main():
                 "per_shape_MKN_us_tflops": [[list(k), round(v[1] / v[0] * 1e3, 1), round(v[2] / v[1] / 1e9, 1)]
                                             for k, v in sorted(per_shape.items())],
             },
+            "other_kernels": other_kernel_rooflines(other_ms, peaks, ms / args.steps),
             "model_tflops": value * executed_gflop_per_image(args.model) / 1e3,
             "model_gflop_per_image_executed": executed_gflop_per_image(args.model),
         }

@@ -109,6 +109,23 @@ def test_large_logits_exercise_the_lazy_rescale(cuda_device):
     assert err <= 2e-2 * max(1.0, mag) and cos >= 0.999, (err, mag, cos)
 
 
+def test_windowed_softmax_when_later_keys_dominate(cuda_device):
+    """Keys of the later window rows are made up to 6x larger than the first rows': whatever reference
+    the kernel subtracts in the exponent has to be the (bound on the) maximum over ALL 196 keys.  (A
+    single-pass variant that took its reference from the first two key rows and rescaled P in TMEM on
+    a jump was measured in round 2 and dropped -- same time as two passes -- but this case stays.)"""
+    B, E, heads, hd = 9, 14, 2, 80
+    qkv, rph, rpw = make_inputs(B, E, heads, hd, seed=11, std=1.0, rp_std=0.3)
+    k = qkv.view(B, E * E, 3, heads, hd)[:, :, 1]
+    k[:, 56:] *= 3.0
+    k[:, 140:] *= 2.0
+    out = ops.attn_relpos(qkv.to(cuda_device), rph.to(cuda_device), rpw.to(cuda_device), B, E, E, heads, hd ** -0.5)
+    ref = oe.attention_core(qkv, rph, rpw, B, E, E, heads, hd ** -0.5, "reference", round_tables=True)
+    err, mag, cos = report(out, ref)
+    assert not torch.isnan(out).any()
+    assert err <= 2e-2 * max(1.0, mag) and cos >= 0.999, (err, mag, cos)
+
+
 @pytest.mark.parametrize("B,E", [(25, 14), (1, 64)])
 @pytest.mark.parametrize("rp_std,tol", [(0.0, 1.0), (0.05, 1.0), (0.3, 1.0), (1.5, 5.0)])
 def test_bound_and_exact_row_maximum_paths(cuda_device, B, E, rp_std, tol):
