@@ -96,6 +96,112 @@ attn_small_kernel(const __half* __restrict__ q, const __half* __restrict__ k, co
   }
 }
 
+// Few keys (image -> tokens: 4096 queries per image, ~9 keys): one THREAD per (batch, head, query), the
+// keys walked sequentially -- a warp per query would keep 9 of 32 lanes busy and launch 2 M warps.
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_fewkeys_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
+                    __half* __restrict__ out, int B, int heads, int Nq, int Nk, float scale_log2e) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * heads * Nq;
+  if (tid >= total) return;
+  // consecutive threads = consecutive heads of one query: their q / out segments are contiguous
+  const int head = static_cast<int>(tid % heads);
+  const int iq = static_cast<int>((tid / heads) % Nq);
+  const int b = static_cast<int>(tid / (static_cast<int64_t>(heads) * Nq));
+  const int D = heads * HD;
+  float qv[HD], acc[HD];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(q + (static_cast<int64_t>(b) * Nq + iq) * D + head * HD);
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = src[c];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        qv[c * 8 + 2 * e] = f.x * scale_log2e;
+        qv[c * 8 + 2 * e + 1] = f.y * scale_log2e;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const __half* kb = k + static_cast<int64_t>(b) * Nk * D + head * HD;
+  const __half* vb = v + static_cast<int64_t>(b) * Nk * D + head * HD;
+  for (int t = 0; t < Nk; ++t) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(t) * D);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = kr[c];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        s = fmaf(qv[c * 8 + 2 * e], f.x, s);
+        s = fmaf(qv[c * 8 + 2 * e + 1], f.y, s);
+      }
+    }
+    const float mn = fmaxf(m, s);
+    const float corr = exp2f(m - mn), p = exp2f(s - mn);
+    m = mn;
+    l = fmaf(l, corr, p);
+    const uint4* vr = reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(t) * D);
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = vr[c];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        acc[c * 8 + 2 * e] = fmaf(acc[c * 8 + 2 * e], corr, p * f.x);
+        acc[c * 8 + 2 * e + 1] = fmaf(acc[c * 8 + 2 * e + 1], corr, p * f.y);
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * Nq + iq) * D + head * HD);
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    __align__(16) __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[c * 8 + 2 * e] * inv, acc[c * 8 + 2 * e + 1] * inv);
+    dst[c] = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// Few reduction terms (K <= 64: the mask product hyper_in . upscaled, K = 32): one THREAD per output.
+__global__ void __launch_bounds__(256)
+small_linear_shortk_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                           const __half* __restrict__ residual, __half* __restrict__ y, int64_t M, int N, int K, int act) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (tid >= M * N) return;
+  const int64_t m = tid / N;
+  const int n = static_cast<int>(tid % N);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + m * K);
+  const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<int64_t>(n) * K);
+  float s = 0.f;
+  for (int c = 0; c < K / 8; ++c) {
+    const uint4 a = xr[c], b = wr[c];
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
+      s = fmaf(fa.x, fb.x, s);
+      s = fmaf(fa.y, fb.y, s);
+    }
+  }
+  if (bias) s += __half2float(bias[n]);
+  if (act == 1) s = 0.5f * s * (1.f + erff(s * 0.70710678118654752440f));
+  else if (act == 2) s = fmaxf(s, 0.f);
+  __half h = __float2half_rn(s);
+  if (residual) h = __hadd(h, residual[m * N + n]);
+  y[m * N + n] = h;
+}
+
 // ---- skinny linear: y[m, n] = act(x[m, :] . w[n, :] + bias[n]) (+ residual[m, n]) --------------
 // x fp16 [M, K], w fp16 [N, K] (nn.Linear layout), fp32 accumulation, any N, K % 8 == 0.
 // One warp per output element pair is wasteful for long M; this kernel is for the decoder's
@@ -174,6 +280,13 @@ extern "C" int samq_attn_small_fwd(const void* q, const void* k, const void* v, 
   const __half *qh = reinterpret_cast<const __half*>(q), *kh = reinterpret_cast<const __half*>(k),
                *vh = reinterpret_cast<const __half*>(v);
   __half* oh = reinterpret_cast<__half*>(out);
+  if (Nk <= 32 && warps >= 4096 && hd <= 32) {     // many queries, few keys: a thread per query
+    const unsigned g2 = static_cast<unsigned>((warps + 127) / 128);
+    if (hd == 16) attn_fewkeys_kernel<16><<<g2, 128, 0, st>>>(qh, kh, vh, oh, B, heads, Nq, Nk, sl);
+    else attn_fewkeys_kernel<32><<<g2, 128, 0, st>>>(qh, kh, vh, oh, B, heads, Nq, Nk, sl);
+    count_launch();
+    return check_launch("attn_fewkeys_kernel");
+  }
   if (hd == 16) attn_small_kernel<16><<<grid, 128, 0, st>>>(qh, kh, vh, oh, B, heads, Nq, Nk, sl);
   else if (hd == 32) attn_small_kernel<32><<<grid, 128, 0, st>>>(qh, kh, vh, oh, B, heads, Nq, Nk, sl);
   else attn_small_kernel<64><<<grid, 128, 0, st>>>(qh, kh, vh, oh, B, heads, Nq, Nk, sl);
@@ -190,6 +303,13 @@ extern "C" int samq_small_linear_fwd(const void* x, const void* w, const void* b
   SAMQ_REQUIRE(act >= 0 && act <= 2, SAMQ_ERR_BAD_ARG, "samq_small_linear_fwd: act=%d", act);
   SAMQ_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0, SAMQ_ERR_BAD_ARG,
                "samq_small_linear_fwd: x and w must be 16-byte aligned");
+  if (K <= 64) {
+    small_linear_shortk_kernel<<<static_cast<unsigned>((M * N + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(w), reinterpret_cast<const __half*>(bias),
+        reinterpret_cast<const __half*>(residual), reinterpret_cast<__half*>(y), M, N, K, act);
+    count_launch();
+    return check_launch("small_linear_shortk_kernel");
+  }
   const int64_t warps = M * N;
   small_linear_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(w), reinterpret_cast<const __half*>(bias),
