@@ -37,6 +37,46 @@ class Sam(nn.Module):
         self.register_buffer("pixel_mean", torch.tensor(pixel_mean).view(-1, 1, 1), persistent=False)
         self.register_buffer("pixel_std", torch.tensor(pixel_std).view(-1, 1, 1), persistent=False)
 
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    def preprocess(self, x: torch.Tensor) -> torch.Tensor:
+        """Normalise the pixel values and zero-pad bottom / right to the encoder's square input (sam.py:164-174)."""
+        x = (x - self.pixel_mean) / self.pixel_std
+        size = self.image_encoder.img_size
+        h, w = x.shape[-2:]
+        return F.pad(x, (0, size - w, 0, size - h))
+
+    def postprocess_masks(self, masks: torch.Tensor, input_size: Tuple[int, ...], original_size: Tuple[int, ...]
+                          ) -> torch.Tensor:
+        """Low-resolution logits -> the original image frame: upsample to the encoder input, cut the
+        padding off, resize to ``original_size`` (sam.py:133-162)."""
+        size = self.image_encoder.img_size
+        masks = F.interpolate(masks, (size, size), mode="bilinear", align_corners=False)
+        masks = masks[..., : input_size[0], : input_size[1]]
+        return F.interpolate(masks, original_size, mode="bilinear", align_corners=False)
+
+    @torch.no_grad()
+    def forward(self, batched_input: List[Dict[str, object]], multimask_output: bool) -> List[Dict[str, torch.Tensor]]:
+        """End to end for a list of images with their prompts (sam.py:53-131).  Every record holds
+        ``image`` (3 x H x W, already resized to the model's frame), ``original_size`` and any of
+        ``point_coords`` + ``point_labels``, ``boxes``, ``mask_inputs``; returns per record ``masks``
+        (bool, original frame), ``iou_predictions`` and ``low_res_logits``.  All images go through the
+        encoder as ONE batch (the fused CUDA path when the encoder is a loaded quantised one)."""
+        dt = next(self.image_encoder.parameters()).dtype
+        images = torch.stack([self.preprocess(rec["image"]) for rec in batched_input], dim=0).to(dt)
+        embeddings = self.image_encoder(images)
+        outputs = []
+        for rec, emb in zip(batched_input, embeddings):
+            points = (rec["point_coords"], rec["point_labels"]) if "point_coords" in rec else None
+            low_res, iou = self.predict_masks(emb.unsqueeze(0), points=points, boxes=rec.get("boxes"),
+                                              mask_input=rec.get("mask_inputs"), multimask_output=multimask_output)
+            masks = self.postprocess_masks(low_res.float(), input_size=rec["image"].shape[-2:],
+                                           original_size=rec["original_size"])
+            outputs.append({"masks": masks > self.mask_threshold, "iou_predictions": iou, "low_res_logits": low_res})
+        return outputs
+
     @torch.no_grad()
     def predict_masks(self, image_embedding: torch.Tensor, points: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                       boxes: Optional[torch.Tensor] = None, mask_input: Optional[torch.Tensor] = None,

@@ -101,3 +101,48 @@ def test_build_sam_module_tree():
               "mask_decoder.output_hypernetworks_mlps.3.layers.2.weight", "mask_decoder.iou_prediction_head.layers.0.weight",
               "mask_decoder.output_upscaling.3.weight", "mask_decoder.transformer.norm_final_attn.weight"):
         assert k in keys, k
+
+
+def test_sam_forward_equals_the_reference_sam(golden_dir):
+    """Sam.forward (preprocess -> encoder -> prompt encoder -> mask decoder -> postprocess) against the
+    REFERENCE's own Sam module on identical weights (strict state-dict load), a depth-1 encoder with a
+    global block (its hard-coded window partition accepts ViT-H batch 1 only), two non-square images with
+    points / boxes.  Needs the staged reference (oracle/_ref); skipped where it is absent."""
+    from oracle import make_ref
+
+    if not make_ref.available():
+        pytest.skip("oracle/_ref is not staged (run `python oracle/make_ref.py` in the build container)")
+    make_ref.add_to_path()
+    from functools import partial
+
+    from segment_anything.modeling import ImageEncoderViT as RefEnc, MaskDecoder as RefDec, PromptEncoder as RefPE
+    from segment_anything.modeling import Sam as RefSam, TwoWayTransformer as RefTT
+
+    torch.manual_seed(3)
+    ours = S.build_sam("vit_b", depth=1, global_attn_indexes=(0,), embed_dim=64, num_heads=2).float().eval()
+    with torch.no_grad():
+        for n, p_ in ours.named_parameters():
+            if "rel_pos" in n or n.endswith("pos_embed"):
+                p_.copy_(torch.randn(p_.shape) * 0.1)
+    ref = RefSam(
+        image_encoder=RefEnc(depth=1, embed_dim=64, img_size=1024, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                             num_heads=2, patch_size=16, qkv_bias=True, use_rel_pos=True, global_attn_indexes=[0],
+                             window_size=14, out_chans=256),
+        prompt_encoder=RefPE(embed_dim=256, image_embedding_size=(64, 64), input_image_size=(1024, 1024), mask_in_chans=16),
+        mask_decoder=RefDec(num_multimask_outputs=3, transformer=RefTT(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                            transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256)).eval()
+    missing = ref.load_state_dict(ours.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(4)
+    batch = [
+        {"image": torch.rand(3, 768, 1024, generator=g) * 255, "original_size": (600, 800),
+         "point_coords": torch.rand(2, 3, 2, generator=g) * 700, "point_labels": torch.randint(0, 2, (2, 3), generator=g).float()},
+        {"image": torch.rand(3, 1024, 640, generator=g) * 255, "original_size": (512, 320),
+         "boxes": torch.tensor([[100.0, 120.0, 400.0, 700.0]])},
+    ]
+    out_o = ours(batch, multimask_output=True)
+    out_r = ref(batch, multimask_output=True)
+    for a, b in zip(out_o, out_r):
+        assert a["masks"].shape == b["masks"].shape and a["masks"].dtype == torch.bool
+        assert torch.allclose(a["low_res_logits"], b["low_res_logits"], atol=2e-4, rtol=1e-3)
+        assert torch.allclose(a["iou_predictions"], b["iou_predictions"], atol=1e-4)
+        assert (a["masks"] != b["masks"]).float().mean().item() < 1e-3

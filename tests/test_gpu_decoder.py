@@ -81,3 +81,49 @@ def test_click_loop_on_the_device(cuda_device):
     r = S.interactive_eval(sam, torch.zeros(1, 3, 1024, 1024, device=cuda_device), gt, num_clicks=5, seed=3,
                            image_embeddings=emb)
     assert r["iou_per_click"].shape == (5, 1) and torch.isfinite(r["low_res_logits"]).all()
+
+
+def test_sam_forward_end_to_end_on_the_device(cuda_device):
+    """Sam.forward on the GPU: preprocess -> GPTQ-int4 encoder on the fused kernels -> prompt encoder ->
+    mask decoder on kernels -> postprocess, against the host chain (oracle encoder on the dequantised
+    weights in fp32 + this package's fp32 decoder path, itself pinned to the reference's modules)."""
+    from oracle import encoder as oe
+    from sam_quantization_b200 import sam as S
+    from sam_quantization_b200.synthetic import random_quantized_encoder
+
+    cfg = dict(embed_dim=256, depth=2, num_heads=4, global_attn_indexes=(1,))
+    enc = random_quantized_encoder("vit_b", 4, 128, seed=1, device=cuda_device, **cfg)
+    pe, md = mk.build_ours()
+    sam_gpu = S.Sam(enc, pe.half(), md.half()).to(cuda_device).eval()
+    g = torch.Generator().manual_seed(8)
+    batch = [
+        {"image": torch.rand(3, 768, 1024, generator=g) * 255, "original_size": (600, 800),
+         "point_coords": torch.rand(2, 2, 2, generator=g) * 700, "point_labels": torch.ones(2, 2)},
+        {"image": torch.rand(3, 1024, 1024, generator=g) * 255, "original_size": (512, 512),
+         "boxes": torch.tensor([[100.0, 120.0, 400.0, 700.0]])},
+    ]
+    to_dev = lambda rec: {k: (v.to(cuda_device) if torch.is_tensor(v) else v) for k, v in rec.items()}
+    launches = _lib.launch_count()
+    out = sam_gpu([to_dev(r) for r in batch], multimask_output=False)
+    assert _lib.launch_count() - launches > 150
+    # host chain on identical weights
+    state = {k.replace(".attn.qkv_proj.", ".attn.qkv.").replace(".attn.o_proj.", ".attn.proj."): v.detach().cpu()
+             for k, v in enc.state_dict().items()}
+    p = oe.dequant_state(state, 4, 128)
+    pe32, md32 = mk.build_ours()
+    host = S.Sam(torch.nn.Module(), pe32, md32)
+    host.image_encoder.img_size = 1024
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for rec, got in zip(batch, out):
+        img = host.preprocess(rec["image"]).half().float().unsqueeze(0)
+        with torch.no_grad():
+            emb = oe.encoder(img, p, cfg["depth"], cfg["num_heads"], cfg["global_attn_indexes"])
+            pts = (rec["point_coords"], rec["point_labels"]) if "point_coords" in rec else None
+            low, iou = host.predict_masks(emb, points=pts, boxes=rec.get("boxes"), multimask_output=False)
+        ref = low.float()
+        err = (got["low_res_logits"].float().cpu() - ref).abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(got["low_res_logits"].float().cpu().flatten().double(),
+                                                    ref.flatten().double(), dim=0).item()
+        print(f"Sam.forward: low-res logits max-abs {err:.3e} (max|ref| {ref.abs().max().item():.3f}) cosine {cos:.6f}")
+        assert err <= 5e-2 * max(1.0, ref.abs().max().item()) and cos >= 0.995
+        assert got["masks"].shape[-2:] == tuple(rec["original_size"]) and got["masks"].dtype == torch.bool
