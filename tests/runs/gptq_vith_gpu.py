@@ -75,6 +75,52 @@ def main():
     res["cosine_rtn_vs_fp16"] = cos(y_rtn, y_fp)
     res["rel_err_gptq"] = float((y_q - y_fp).norm() / y_fp.norm())
     res["rel_err_rtn"] = float((y_rtn - y_fp).norm() / y_fp.norm())
+    # the reference's own solver (gptq.py, torch ops on the same GPU, one column at a time) on the four
+    # layer shapes of a ViT-H block with the same kind of input, for the record
+    try:
+        from oracle import make_ref
+
+        make_ref.add_to_path()
+        import gptq as ref_gptq            # the staged reference module (oracle/_ref/gptq.py)
+
+        D = enc.blocks[0].norm1.weight.numel()
+        shapes = {"qkv": (D, 3 * D), "proj": (D, D), "lin1": (D, 4 * D), "lin2": (4 * D, D)}
+        t_ref = t_ours = 0.0
+        for name, (k, n) in shapes.items():
+            x = (torch.randn(1, 4096, k, device=dev, generator=torch.Generator(dev).manual_seed(k + n)) *
+                 torch.linspace(0.3, 2.0, k, device=dev)).half()
+            w = torch.randn(n, k, device=dev, generator=torch.Generator(dev).manual_seed(n)) * 0.02
+            for which in ("ref", "ours"):
+                lin = torch.nn.Linear(k, n, bias=False).to(dev)
+                lin.weight.data = w.clone()
+                if which == "ref":
+                    s_ = ref_gptq.GPTQ(lin)
+                    s_.quantizer = ref_gptq.Quantizer()
+                else:
+                    s_ = G.GPTQ(lin)
+                    s_.quantizer = G.Quantizer()
+                s_.quantizer.configure(4, perchannel=True, sym=False, mse=False)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                s_.add_batch(x, None)
+                s_.fasterquant(percdamp=0.01, groupsize=128)
+                torch.cuda.synchronize()
+                dt = time.time() - t0
+                xf = x[0].float()
+                out_err = float((xf @ (lin.weight.data.float() - w).t()).norm() / (xf @ w.t()).norm())
+                if which == "ref":
+                    t_ref += dt
+                    q_ref = lin.weight.data.clone()
+                    res[f"{name}_layer_output_rel_err_reference_solver"] = out_err
+                else:
+                    t_ours += dt
+                    flips = ((lin.weight.data - q_ref).abs() > 1e-6).float().mean().item()
+                    res[f"{name}_rounded_weight_mismatch_vs_reference_solver"] = flips
+                    res[f"{name}_layer_output_rel_err_device_solver"] = out_err
+        res["one_block_reference_solver_s"] = round(t_ref, 3)
+        res["one_block_device_solver_s"] = round(t_ours, 3)
+    except Exception as ex:      # the staged reference is optional
+        res["reference_solver"] = f"not run: {ex!r}"
     print(json.dumps(res, indent=1))
     with open(out_path, "w") as f:
         json.dump(res, f, indent=1)
