@@ -216,6 +216,61 @@ def make_encoder_q4_fixture():
     print("encoder q4 fixture", y.shape, float(np.abs(y).max()))
 
 
+def extract_generic_partition():
+    """The reference's own GENERIC window_partition / window_unpartition (fq_vit/models/sam/image_encoder.py:
+    481-537; the copies in segment_anything are hard-coded to ViT-H batch 1), AST-extracted because the fq_vit
+    package imports quantisation tooling that is not installed."""
+    src = open(os.path.join(REF, "fq_vit/models/sam/image_encoder.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "F": torch.nn.functional, "Tuple": __import__("typing").Tuple}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("window_partition", "window_unpartition"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "fq_vit_image_encoder", "exec"), ns)
+    return ns["window_partition"], ns["window_unpartition"]
+
+
+def make_encoder_vitl_b2_fixture():
+    """Pins what the hard-coded partition cannot: another width and batch > 1.  Reference ImageEncoderViT at
+    ViT-L width (1024, 16 heads of 64), depth 2 (windowed + global), BATCH 2, fp32, with the reference's own
+    generic partition functions patched in and dequantised int4-g128 weights in its nn.Linears."""
+    from functools import partial
+
+    import segment_anything.modeling.image_encoder as rie
+    from oracle import encoder as oe
+
+    part, unpart = extract_generic_partition()
+    saved = rie.window_partition, rie.window_unpartition
+    rie.window_partition, rie.window_unpartition = part, unpart
+    try:
+        cfg = dict(embed_dim=1024, depth=2, num_heads=16, global_attn_indexes=(1,))
+        enc = rie.ImageEncoderViT(img_size=1024, patch_size=16, embed_dim=1024, depth=2, num_heads=16, mlp_ratio=4,
+                                  out_chans=256, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                                  use_rel_pos=True, window_size=14, global_attn_indexes=(1,))
+        p = synth.fp_state(seed=9, **cfg)
+        rng = np.random.default_rng(29)
+        for k in p:
+            if "rel_pos" in k:
+                p[k] = (rng.standard_normal(p[k].shape) * 0.2).astype(np.float32)
+        state = oe.dequant_state(synth.to_torch(synth.quantize_state(p, 4, 128)), 4, 128)
+        enc.load_state_dict(state, strict=True)
+        img = synth.image(2, 1024, seed=9).astype(np.float16).astype(np.float32)
+        grabbed = {}
+        hooks = [enc.blocks[i].register_forward_hook(lambda _m, _i, o, i=i: grabbed.__setitem__(i, o.detach().numpy()))
+                 for i in range(2)]
+        with torch.no_grad():
+            y = enc(torch.from_numpy(img)).numpy()
+        for h in hooks:
+            h.remove()
+    finally:
+        rie.window_partition, rie.window_unpartition = saved
+    np.savez_compressed(os.path.join(HERE, "encoder_vitl_d2_b2_q4.npz"), y_sub=y[:, :, ::4, ::4].astype(np.float32),
+                        y_mean=np.float64(y.mean()), y_absmax=np.float64(np.abs(y).max()),
+                        tok0_sub=grabbed[0][:, ::4, ::4, ::8].astype(np.float32), tok0_absmax=np.float64(np.abs(grabbed[0]).max()),
+                        tok1_sub=grabbed[1][:, ::4, ::4, ::8].astype(np.float32), tok1_absmax=np.float64(np.abs(grabbed[1]).max()),
+                        seed=9, relpos_seed=29, bits=4, groupsize=128, batch=2)
+    print("encoder ViT-L batch-2 fixture", y.shape, float(np.abs(y).max()))
+
+
 def make_relpos_fixture():
     """Reference get_rel_pos (image_encoder.py:336-366) incl. its interpolation branch (:348-358): tables
     whose length differs from 2 * max(q, k) - 1, and non-square q / k."""
@@ -235,6 +290,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder_q4":
         make_encoder_q4_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "vitl_b2":
+        make_encoder_vitl_b2_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "relpos":
         make_relpos_fixture()
         sys.exit(0)
@@ -246,4 +304,5 @@ if __name__ == "__main__":
     make_encoder_fixture()
     make_encoder_q4_fixture()
     make_relpos_fixture()
+    make_encoder_vitl_b2_fixture()
     print("done")

@@ -189,9 +189,9 @@ def test_gptq_calibrated_encoder_on_the_cuda_path(cuda_device, tmp_path):
     assert err <= 6e-2 * max(1.0, mag) and cos >= 0.999, (err, mag, cos)
 
 
-def _vith_d2_q4(golden_dir, tmp_path, device):
-    g = np.load(os.path.join(golden_dir, "encoder_vith_d2_q4.npz"))
-    cfg = dict(embed_dim=1280, depth=2, num_heads=16, global_attn_indexes=(1,))
+def _vith_d2_q4(golden_dir, tmp_path, device, fixture="encoder_vith_d2_q4.npz", embed_dim=1280):
+    g = np.load(os.path.join(golden_dir, fixture))
+    cfg = dict(embed_dim=embed_dim, depth=2, num_heads=16, global_attn_indexes=(1,))
     p = synth.fp_state(seed=int(g["seed"]), **cfg)
     rng = np.random.default_rng(int(g["relpos_seed"]))
     for k in p:
@@ -237,6 +237,32 @@ def test_vith_width_encoder_against_the_reference_modules_output(cuda_device, go
     print(f"embedding: max-abs {err:.3e} (max|ref| {float(g['y_absmax']):.2f}) cosine {cos:.7f}")
     assert err <= 6e-2 and cos >= 0.999
     assert abs(float(y.mean()) - float(g["y_mean"])) < 2e-3
+
+
+def test_vitl_width_batch2_encoder_against_the_reference_modules_output(cuda_device, golden_dir, tmp_path):
+    """What the reference's hard-coded partition cannot run is pinned to the reference all the same: its
+    ImageEncoderViT with its OWN generic window_partition / window_unpartition (fq_vit/models/sam/
+    image_encoder.py:481-537) patched in, ViT-L width (1024, heads of 64), batch 2, dequantised int4-g128
+    weights (tests/golden/encoder_vitl_d2_b2_q4.npz).  Same tolerances as the ViT-H fixture test."""
+    g, enc, _ = _vith_d2_q4(golden_dir, tmp_path, cuda_device, "encoder_vitl_d2_b2_q4.npz", 1024)
+    img = torch.from_numpy(synth.image(2, 1024, seed=int(g["seed"]))).half().to(cuda_device)
+    grabbed = {}
+    hooks = [enc.blocks[i].register_forward_hook(lambda _m, _i, o, i=i: grabbed.__setitem__(i, o.detach().float().cpu()))
+             for i in range(2)]
+    with torch.no_grad():
+        y = enc(img).float().cpu()
+    for h in hooks:
+        h.remove()
+    for i in range(2):
+        sub, ref = grabbed[i][:, ::4, ::4, ::8], torch.from_numpy(g[f"tok{i}_sub"])
+        err = (sub - ref).abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(sub.flatten().double(), ref.flatten().double(), dim=0).item()
+        print(f"ViT-L batch 2, block {i}: max-abs {err:.3e} (max|ref| {float(g[f'tok{i}_absmax']):.2f}) cosine {cos:.7f}")
+        assert err <= 1.5e-2 * float(g[f"tok{i}_absmax"]) and cos >= 0.9999
+    sub, ref = y[:, :, ::4, ::4], torch.from_numpy(g["y_sub"])
+    err = (sub - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(sub.flatten().double(), ref.flatten().double(), dim=0).item()
+    assert err <= 6e-2 and cos >= 0.999, (err, cos)
 
 
 def test_vith_width_blocks_at_the_benchmarked_batch(cuda_device, golden_dir, tmp_path):
