@@ -209,8 +209,12 @@ __device__ __forceinline__ void ln_token_from_regs(const uint4 (&raw)[NVEC], con
 
 // PARTITION == false: rows are tokens of x;  true: rows are OUTPUT tokens of the windowed
 // layout [B*nH*nW, ws, ws, C] (source token looked up, padding written as zeros).
+// Three resident blocks per SM for C <= 1280 (<= 80 registers): in situ, behind the power-capped GEMMs at
+// ~1.35 GHz, the reduce / normalise phase of a warp takes 35 % longer than at the 1.8 GHz ncu sees, and 16
+// warps per SM no longer cover it (A/B on one box: 131 -> 118 us per 131072 x 1280 call, + 0.4 % of the step;
+// one token per warp at four blocks per SM: 124 us).
 template <int NVEC, bool PARTITION>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NVEC <= 5 ? 3 : 2)
 layernorm_fast_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                       const __half* __restrict__ beta, __half* __restrict__ y, int64_t rows, int B,
                       int H, int W, int ws, int nH, int nW, float eps) {
