@@ -281,16 +281,27 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
         if (relw_mode != SAMQ_RELW_UPSTREAM) {
           // both tables are indexed by the image row: one pass over the warp's (<= 4) image rows
 #pragma unroll 1
-          for (int v = vh_lo; v <= vh_hi; ++v) {
-            uint32_t rh[16], rv[16];
+          for (int v = vh_lo; v <= vh_hi; v += 2) {
+            // two image rows per wait (the second one clamped: a duplicate load when the count is odd)
+            const int v2 = min(v + 1, vh_hi);
+            uint32_t rh[16], rv[16], rh2[16], rv2[16];
             tmem_ld_x16(region + v, rh);
             tmem_ld_x16(region + 32 + v, rv);
+            tmem_ld_x16(region + v2, rh2);
+            tmem_ld_x16(region + 32 + v2, rv2);
             tmem_ld_wait();
             if (mh == v) {
 #pragma unroll
               for (int k = 0; k < E; ++k) {
                 bh[k] = __uint_as_float(rh[13 - k]);
                 bw[k] = __uint_as_float(rv[13 - k]);
+              }
+            }
+            if (mh == v2) {
+#pragma unroll
+              for (int k = 0; k < E; ++k) {
+                bh[k] = __uint_as_float(rh2[13 - k]);
+                bw[k] = __uint_as_float(rv2[13 - k]);
               }
             }
           }
@@ -477,23 +488,22 @@ attn_win3_kernel(const __grid_constant__ CUtensorMap map_qa_main, const __grid_c
           o.w = pack_h2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
           return o;
         };
+        // all of O in flight at once, ONE wait (tcgen05.wait::ld waits for every outstanding load, so
+        // a load / wait pair per chunk paid the TMEM latency three times)
+        uint32_t r0[32], r1[32], r2[16];
+        tmem_ld_x32(o_tmem, r0);
+        tmem_ld_x32(o_tmem + 32, r1);
+        if (C::kTail) tmem_ld_x16(o_tmem + 64, r2);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(o_tmem + c * 32, r);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) o_row[c * 4 + v] = pack8(r + 8 * v);
+          for (int v = 0; v < 4; ++v) {
+            o_row[v] = pack8(r0 + 8 * v);
+            o_row[4 + v] = pack8(r1 + 8 * v);
           }
-        }
-        if (C::kTail) {
-          uint32_t r[16];
-          tmem_ld_x16(o_tmem + 64, r);
-          tmem_ld_wait();
-          if (valid) {
-            o_row[8] = pack8(r);
-            o_row[9] = pack8(r + 8);
+          if (C::kTail) {
+            o_row[8] = pack8(r2);
+            o_row[9] = pack8(r2 + 8);
           }
         }
       }
