@@ -3,6 +3,7 @@
 // smem / TMEM).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu
 #include "../../sam_quantization_b200/csrc/common.cuh"
 #include <cstdio>
+#include <cstdlib>
 using namespace samq;
 
 template <bool TS, bool PAIR>
@@ -124,8 +125,14 @@ void run(const char* name, int n, int per_commit) {
 
 int main() {
   setvbuf(stdout, nullptr, _IONBF, 0);
-  for (int delay : {0, 100, 200, 300, 400, 600}) run_delay(192, delay, 0);
-  for (int waits : {1, 2, 3}) run_delay(192, 0, waits);
+  if (getenv("UMMA_DELAY")) {
+    for (int delay : {0, 100, 200, 300, 400, 600}) run_delay(192, delay, 0);
+    for (int waits : {1, 2, 3}) run_delay(192, 0, waits);
+  }
+  for (int n : {16, 32, 48, 80, 96}) {
+    run<false, false>("SS 1cta", n, 64);
+    run<true, false>("TS 1cta", n, 64);
+  }
   for (int pc : {64}) {
     for (int n : {64, 128, 192, 256}) {
       run<false, false>("SS 1cta", n, pc);
