@@ -7,6 +7,19 @@
 #include "../../sam_quantization_b200/csrc/attention_glob.cu"
 #include <cstdio>
 #include <vector>
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+// SM clock right now: one block spinning for a fixed number of clock64 ticks, timed with events
+static double sm_mhz() {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  spin_kernel<<<1, 32>>>(2000000);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  return 2000000.0 / (ms * 1e3);
+}
 int main(int argc, char** argv) {
   const int hd = argc > 1 ? atoi(argv[1]) : 80;
   const int B = argc > 2 ? atoi(argv[2]) : 8;
@@ -24,13 +37,15 @@ int main(int argc, char** argv) {
   cudaMemcpy(rph, rp.data(), rp.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(rpw, rp.data(), rp.size() * 2, cudaMemcpyHostToDevice);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int it = 0; it < 3; ++it) {
+  const int iters = argc > 4 ? atoi(argv[4]) : 3;
+  for (int it = 0; it < iters; ++it) {
     cudaEventRecord(e0);
     int rc = samq_attn_relpos_fwd(qkv, rph, rpw, out, B, E, E, heads, hd, 1.f / sqrtf(hd), 0, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    printf("rc %d  %.1f us  (%s)\n", rc, ms * 1e3, cudaGetErrorString(cudaGetLastError()));
+    if (it < 3 || it == iters - 1) printf("rc %d  %.1f us  (%s)\n", rc, ms * 1e3, cudaGetErrorString(cudaGetLastError()));
   }
+  printf("SM clock after the runs: %.0f MHz\n", sm_mhz());
 #ifdef SAMQ_ATTN_PROFILE
   long long prof[12][8];
   cudaMemcpyFromSymbol(prof, samq::g_attn_prof, sizeof(prof));
