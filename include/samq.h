@@ -57,7 +57,8 @@ typedef enum samq_relw_mode {
 /* ABI version of this header (bumped on any signature change or new entry point).
  * 1: round 1.  2: single-FMA dequant (the reference's Triton rounding), samq_config_reload /
  * samq_has_ablations.  3: samq_gather_cols_fwd, samq_syrk_f32_fwd, samq_gptq_block_fwd,
- * samq_attn_small_fwd, samq_small_linear_fwd, samq_gelu_fwd. */
+ * samq_attn_small_fwd, samq_small_linear_fwd, samq_gelu_fwd.  4: samq_qlinear_prefetch; the
+ * samq_qlinear_* entry points accept NULL packed pointers + a prefetched workspace. */
 int samq_abi_version(void);
 
 /* Reason for the last non-OK status returned to the calling thread. */
@@ -174,6 +175,17 @@ int samq_qlinear_fwd(const void* x, const int32_t* qweight, const int32_t* qzero
                      const void* residual, void* y, void* workspace,
                      int64_t M, int K, int N, int bits, int groupsize,
                      int epilogue, void* stream);
+
+/* Weight prefetch for the unpack-once path (int4, contiguous groups): unpacks the packed weight of
+ * the NEXT QuantLinear into `workspace` (fp16 Wt[N, K]) with a small persistent grid that is launched
+ * programmatically behind the kernel enqueued before it -- normally the current layer's GEMM -- and
+ * runs NEXT TO it instead of between two GEMMs.  `workspace` must not be read by any kernel still in
+ * flight on the stream (the host rotates three buffers).  The prefetched weight is consumed by calling
+ * samq_qlinear_fwd / samq_qlinear_unpartition_fwd / samq_qlinear_partition_fwd with
+ * qweight == qzeros == scales == g_idx == NULL and the same `workspace`: they then run only the dense
+ * tcgen05 GEMM.  Same arithmetic and bits as samq_unpack_dequant (quant_linear.py:291-301, 334-339). */
+int samq_qlinear_prefetch(const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                          void* workspace, int K, int N, int bits, int groupsize, void* stream);
 
 /* proj GEMM fused with window_unpartition + crop + residual add
  * (QuantAttention.forward's o_proj, fused_attention.py:147, followed by

@@ -69,6 +69,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     ),
+    "samq_qlinear_prefetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "samq_dense_linear_fwd": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
@@ -124,6 +125,7 @@ def load() -> ctypes.CDLL:
 #:   SAMQ_GEMM=fused|dense   force one int4 QuantLinear path (the library reads the same variable)
 #:   SAMQ_PAD_SKIP=0         windowed blocks partition first and multiply the zero-padding rows
 #:   SAMQ_NECK_CONV=cudnn    neck conv3x3 through cuDNN instead of im2col + tcgen05 GEMM
+#:   SAMQ_PREFETCH=0         no weight prefetch: every QuantLinear unpacks its own weight right before its GEMM
 OPTIONS = {}
 
 
@@ -131,6 +133,7 @@ def _read_options() -> None:
     OPTIONS["gemm"] = os.environ.get("SAMQ_GEMM", "")
     OPTIONS["pad_skip"] = os.environ.get("SAMQ_PAD_SKIP", "1") != "0"
     OPTIONS["neck_cudnn"] = os.environ.get("SAMQ_NECK_CONV", "") == "cudnn"
+    OPTIONS["prefetch"] = os.environ.get("SAMQ_PREFETCH", "1") != "0"
 
 
 _read_options()

@@ -130,20 +130,14 @@ unpack_dequant_kernel(const int32_t* __restrict__ qweight, const int32_t* __rest
 // one packed row touch whole 32-byte sectors (8 consecutive n); the 4 lanes of a feature write
 // 128 contiguous bytes.  Same arithmetic as above, on fp16 pairs (lop3 / add / fma), so the
 // result is bit-identical to the generic kernel and to the fused GEMM's operand.
-__global__ void __launch_bounds__(256)
-dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
-                           const __half* __restrict__ scales, __half* __restrict__ wt, int K, int N,
-                           int groupsize) {
-  // programmatic dependent launch: the GEMM that consumes Wt may be scheduled right away; it
-  // blocks in griddepcontrol.wait (after its barrier / TMEM set-up) until this grid has completed
-  pdl_trigger();
-  const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// one warp item: 8 output features x 64 k of Wt
+__device__ __forceinline__ void dequant4_item(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                                              const __half* __restrict__ scales, int K, int N, int groupsize,
+                                              int warp_global, int lane, uint32_t (&out)[8], int64_t& dst_off) {
   const int kblocks = K >> 6;                          // 64-k blocks
   const int nb = warp_global / kblocks, kb = warp_global - nb * kblocks;
   const int n = nb * 8 + (lane & 7);
   const int k0 = kb * 64 + (lane >> 3) * 16;
-  if (n >= N) return;
   const int g = k0 / groupsize;
   const __half s = scales[static_cast<int64_t>(g) * N + n];
   const uint32_t zw = static_cast<uint32_t>(qzeros[static_cast<int64_t>(g) * (N >> 3) + (n >> 3)]);
@@ -151,7 +145,6 @@ dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* _
   const __half zs = __hmul_rn(__uint2half_rn(z + 1u), s);
   const uint32_t su = __half_as_ushort(s), s2 = su | (su << 16);
   const uint32_t zu = __half_as_ushort(__hneg(zs)), nzs2 = zu | (zu << 16);
-  uint32_t out[8];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const uint32_t w = static_cast<uint32_t>(qweight[static_cast<int64_t>((k0 >> 3) + r) * N + n]);
@@ -169,11 +162,62 @@ dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* _
     asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(out[4 * r + 2]) : "r"(q4[0]), "r"(q4[1]));
     asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(out[4 * r + 3]) : "r"(q4[2]), "r"(q4[3]));
   }
+  dst_off = static_cast<int64_t>(n) * K + k0;
+}
+
+__global__ void __launch_bounds__(256)
+dequant4_transposed_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                           const __half* __restrict__ scales, __half* __restrict__ wt, int K, int N,
+                           int groupsize) {
+  // programmatic dependent launch: the GEMM that consumes Wt may be scheduled right away; it
+  // blocks in griddepcontrol.wait (after its barrier / TMEM set-up) until this grid has completed
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp_global >= (N >> 3) * (K >> 6)) return;
+  uint32_t out[8];
+  int64_t off;
+  dequant4_item(qweight, qzeros, scales, K, N, groupsize, warp_global, lane, out, off);
   // (the packed weights are constant; the scratch Wt may still be read by an earlier GEMM)
   pdl_wait();
-  uint4* dst = reinterpret_cast<uint4*>(wt + static_cast<int64_t>(n) * K + k0);
+  uint4* dst = reinterpret_cast<uint4*>(wt + off);
   dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
   dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+// The same unpack as a PREFETCH of the NEXT layer's weight: launched (programmatically) right behind
+// the current layer's GEMM, it runs next to it -- ONE small block per SM (8 k registers, no shared
+// memory: what is left beside the 168-register GEMM; a second block per SM would not be resident, and since
+// every block stays until the GEMM is done -- the final wait -- it would only start after the GEMM) fits beside the
+// GEMM's one persistent CTA, looping over the work -- and writes a
+// scratch buffer that no kernel in flight reads (the host rotates three).  It still ends with
+// griddepcontrol.wait, so that "this grid has completed" keeps implying "everything before it has
+// completed" for the kernel launched behind it.
+__global__ void __launch_bounds__(256, 6)   // <= 40 registers: 10 k per block, beside the GEMM's 53.8 k of the SM's 64 k
+dequant4_transposed_prefetch_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                                    const __half* __restrict__ scales, __half* __restrict__ wt, int K, int N,
+                                    int groupsize) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int total = (N >> 3) * (K >> 6);
+  const int stride = gridDim.x * (blockDim.x >> 5);
+  // two items per trip: both items' loads are issued before either is converted
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += 2 * stride) {
+    uint32_t out_a[8], out_b[8];
+    int64_t off_a, off_b = 0;
+    const bool two = w + stride < total;
+    dequant4_item(qweight, qzeros, scales, K, N, groupsize, w, lane, out_a, off_a);
+    if (two) dequant4_item(qweight, qzeros, scales, K, N, groupsize, w + stride, lane, out_b, off_b);
+    uint4* dst = reinterpret_cast<uint4*>(wt + off_a);
+    dst[0] = make_uint4(out_a[0], out_a[1], out_a[2], out_a[3]);
+    dst[1] = make_uint4(out_a[4], out_a[5], out_a[6], out_a[7]);
+    if (two) {
+      dst = reinterpret_cast<uint4*>(wt + off_b);
+      dst[0] = make_uint4(out_b[0], out_b[1], out_b[2], out_b[3]);
+      dst[1] = make_uint4(out_b[4], out_b[5], out_b[6], out_b[7]);
+    }
+  }
+  pdl_wait();
 }
 
 // ---- fast path for every format, transposed output Wt[N, K] (feeds the dense tcgen05 GEMM) -------
@@ -269,6 +313,25 @@ static int launch_unpack(const int32_t* qweight, const int32_t* qzeros, const __
     unpack_dequant_kernel<BITS, false><<<grid, block, 0, st>>>(qweight, qzeros, scales, g_idx, w_out, K, N, groupsize);
   count_launch();
   return check_launch("unpack_dequant_kernel");
+}
+
+// int4, contiguous groups: unpack into `w_out` [N, K] NEXT TO the kernel launched before this one
+// (see dequant4_transposed_prefetch_kernel); w_out must not be read by any kernel still in flight
+int prefetch_dequant4(const int32_t* qweight, const int32_t* qzeros, const void* scales, void* w_out, int K, int N,
+                      int groupsize, int num_sms, cudaStream_t st) {
+  SAMQ_REQUIRE(qweight && qzeros && scales && w_out, SAMQ_ERR_BAD_ARG, "qlinear_prefetch: null pointer");
+  if (groupsize == -1) groupsize = K;
+  SAMQ_REQUIRE(K > 0 && N > 0 && K % 64 == 0 && N % 8 == 0 && groupsize > 0 && groupsize % 16 == 0 && K % groupsize == 0,
+               SAMQ_ERR_BAD_SHAPE, "qlinear_prefetch: K=%d N=%d groupsize=%d (K %% 64, N %% 8, groupsize %% 16 == 0)", K, N,
+               groupsize);
+  SAMQ_REQUIRE(reinterpret_cast<uintptr_t>(w_out) % 16 == 0, SAMQ_ERR_BAD_ARG, "qlinear_prefetch: w_out must be 16-byte aligned");
+  const int warps = (N / 8) * (K / 64);
+  const int blocks = (warps + 7) / 8;
+  const int grid = blocks < num_sms ? blocks : num_sms;
+  launch_pdl(1, dequant4_transposed_prefetch_kernel, dim3(grid), dim3(256), 0, st, qweight, qzeros,
+             reinterpret_cast<const __half*>(scales), reinterpret_cast<__half*>(w_out), K, N, groupsize);
+  count_launch();
+  return check_launch("dequant4_transposed_prefetch_kernel");
 }
 
 int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* scales,

@@ -40,6 +40,8 @@ int launch_qlinear_pair(const void* x, const void* qweight, const __half* scales
 int launch_dense_pair(const void* x, const void* wt, const __half* bias, const __half* residual, __half* y,
                       int64_t M, int K, int N, int epilogue, const RowMap& rowmap, int num_sms, cudaStream_t st);
 
+int prefetch_dequant4(const int32_t* qweight, const int32_t* qzeros, const void* scales, void* w_out, int K, int N,
+                      int groupsize, int num_sms, cudaStream_t st);
 int unpack_dequant(const int32_t* qweight, const int32_t* qzeros, const void* scales,
                    const int32_t* g_idx, void* w_out, int K, int N, int bits, int groupsize,
                    int transposed, cudaStream_t st);
@@ -363,6 +365,13 @@ int qlinear_impl(const char* who, const void* x, const int32_t* qweight, const i
                "%s: bits must be 2, 3, 4 or 8 (got %d)", who, bits);
   int rc = check_common(x, y, M, K, N, epilogue, who);
   if (rc != SAMQ_OK) return rc;
+  if (!qweight && !qzeros && !scales && !g_idx) {
+    // the weight was unpacked ahead of time (samq_qlinear_prefetch): `workspace` holds fp16 Wt[N, K]
+    SAMQ_REQUIRE(workspace && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, SAMQ_ERR_BAD_ARG,
+                 "%s: no packed weight and no 16-byte aligned prefetched workspace", who);
+    return launch_dense(x, workspace, reinterpret_cast<const __half*>(bias), reinterpret_cast<const __half*>(residual),
+                        reinterpret_cast<__half*>(y), M, K, N, epilogue, rowmap, st);
+  }
   SAMQ_REQUIRE(qweight && qzeros && scales, SAMQ_ERR_BAD_ARG, "%s: null weight pointer", who);
   if (groupsize == -1) groupsize = K;
   SAMQ_REQUIRE(groupsize > 0 && K % groupsize == 0, SAMQ_ERR_BAD_SHAPE,
@@ -547,15 +556,23 @@ extern "C" int samq_qlinear_partition_fwd(const void* x, const int32_t* qweight,
   const int64_t M_img = static_cast<int64_t>(B) * H * W;
   const RowMap to_win = {ws, H, W, nH, nW, 1};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc = qlinear_impl("samq_qlinear_partition_fwd", x, qweight, qzeros, scales, g_idx, bias, nullptr, y, workspace,
-                        M_img, K, N, bits, groupsize, SAMQ_EPI_NONE, to_win, st);
-  if (rc != SAMQ_OK) return rc;
+  SAMQ_REQUIRE(y != nullptr, SAMQ_ERR_BAD_ARG, "samq_qlinear_partition_fwd: null output");
+  // pad rows first (they are disjoint from the rows the GEMM stores): the GEMM is then the LAST kernel
+  // of this call, and a weight prefetch launched behind it runs next to it
   if (nH * ws != H || nW * ws != W) {
     const int64_t pad_rows = static_cast<int64_t>(B) * (H * (nW * ws - W) + (nH * ws - H) * nW * ws);
     fill_pad_rows_kernel<<<static_cast<unsigned>((pad_rows + 7) / 8), 256, 0, st>>>(
         reinterpret_cast<__half*>(y), reinterpret_cast<const __half*>(bias), B, N, to_win);
     count_launch();
-    return check_launch("fill_pad_rows_kernel");
+    if (int rc = check_launch("fill_pad_rows_kernel"); rc != SAMQ_OK) return rc;
   }
-  return SAMQ_OK;
+  return qlinear_impl("samq_qlinear_partition_fwd", x, qweight, qzeros, scales, g_idx, bias, nullptr, y, workspace,
+                      M_img, K, N, bits, groupsize, SAMQ_EPI_NONE, to_win, st);
+}
+
+extern "C" int samq_qlinear_prefetch(const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                                     void* workspace, int K, int N, int bits, int groupsize, void* stream) {
+  using namespace samq;
+  SAMQ_REQUIRE(bits == 4, SAMQ_ERR_UNSUPPORTED_BITS, "samq_qlinear_prefetch: int4 only (got %d bits)", bits);
+  return prefetch_dequant4(qweight, qzeros, scales, workspace, K, N, groupsize, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }

@@ -229,7 +229,7 @@ const CUtensorMap* get_tensor_map_2d(const void* base, uint64_t rows, uint64_t c
 // ---------------------------------------------------------------------------
 extern "C" {
 
-int samq_abi_version(void) { return 3; }
+int samq_abi_version(void) { return 4; }
 
 void samq_config_reload(void) {
   (void)samq::config();

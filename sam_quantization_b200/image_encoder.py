@@ -35,7 +35,7 @@ import torch.nn.functional as F
 from . import _lib, ops
 from .fused_attention import QuantAttention
 from .fused_mlp import QuantMLP
-from .quant_linear import QuantLinear
+from .quant_linear import QuantLinear, WeightPrefetchChain
 
 __all__ = [
     "ImageEncoderViT", "Block", "Attention", "MLPBlock", "PatchEmbed", "LayerNorm2d",
@@ -299,8 +299,24 @@ class ImageEncoderViT(nn.Module):
             LayerNorm2d(out_chans),
         )
 
+    def _prefetch_chain(self, x: torch.Tensor):
+        """The quantized linears of the fused blocks in execution order, linked so that each one's
+        GEMM is followed by the unpack of the next one's weight (``WeightPrefetchChain``)."""
+        layers = []
+        for blk in self.blocks:
+            if blk._fused_ready():
+                layers += [blk.attn.qkv_proj, blk.attn.o_proj, blk.mlp.lin1, blk.mlp.lin2]
+        chain = self.__dict__.get("_pf_chain")
+        if chain is None or chain.key != tuple(id(m) for m in layers):
+            chain = WeightPrefetchChain(layers)
+            self.__dict__["_pf_chain"] = chain
+        chain.begin(x.device)
+        return chain
+
     def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """The 32-block hot loop on tokens ``[B, 64, 64, D]`` (image_encoder.py:111-113)."""
+        if x.is_cuda and x.dtype == torch.float16:
+            self._prefetch_chain(x)
         for blk in self.blocks:
             x = blk(x)
         return x

@@ -19,6 +19,7 @@ Differences from the reference, all deliberate:
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional
 
 import warnings
@@ -91,6 +92,83 @@ def unpack_fields(words: torch.Tensor, bits: int) -> torch.Tensor:
             fields.append(v & 7)
         return torch.stack(fields, dim=1).reshape(rows // 3 * 32, cols)
     raise NotImplementedError("Only 2,3,4,8 bits are supported.")
+
+
+class WeightPrefetchChain:
+    """Weight prefetch over a fixed execution order of int4 ``QuantLinear`` layers (the four linears of
+    every encoder block).  For long M a layer runs as "unpack the weight once into an fp16 scratch, then
+    a dense tcgen05 GEMM"; done back to back, the 6 us unpack kernel sits BETWEEN two GEMMs with the GPU
+    nearly idle.  With a chain, right after layer i's GEMM has been enqueued the unpack of layer i + 1
+    is launched programmatically behind it (``samq_qlinear_prefetch``): a small persistent grid that
+    runs next to that GEMM and writes one of ``kBuffers`` rotating scratch buffers; layer i + 1 then
+    only runs its GEMM.  Same kernels' arithmetic, same results bit for bit.
+
+    Why the early writes are safe: a scratch buffer is rewritten kBuffers - 1 prefetches after the GEMM
+    that read it, and in the encoder at most two GEMMs follow each other without a normally launched
+    kernel (LayerNorm, attention) between them, which completes everything before it.  The buffers are
+    allocated once, before any operand of a kernel that can overlap a prefetch (so the caching
+    allocator cannot hand them memory such a kernel still reads), and never re-allocated.
+
+    State lives here and in a weak map, not on the modules: ``state_dict``, ``deepcopy`` and pickling of
+    the model are unaffected."""
+
+    kBuffers = 4
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+        self.key = tuple(id(m) for m in self.layers)
+        self.bufs = None
+        self.slot = 0
+        self.ready = None          # (index, buffer, weight version key) of the one prefetched layer
+        for i, m in enumerate(self.layers):
+            _PREFETCH[m] = (self, i)
+
+    def __deepcopy__(self, memo):   # a copied encoder links its own chain on first use
+        return None
+
+    @staticmethod
+    def _version(m):
+        return (m.qweight.data_ptr(), m.qweight._version, m.qzeros.data_ptr(), m.qzeros._version,
+                m.scales.data_ptr(), m.scales._version)
+
+    @staticmethod
+    def _prefetchable(m) -> bool:
+        return (isinstance(m, QuantLinear) and m.bits == 4 and m.g_idx is None and m.groupsize % 16 == 0
+                and m.infeatures % 64 == 0 and m.outfeatures % 8 == 0 and m.qweight.is_cuda)
+
+    def begin(self, device) -> None:
+        """Start of a pass over the chain: drop stale state, make sure the scratch buffers exist."""
+        self.ready = None
+        numel = max((m.infeatures * m.outfeatures for m in self.layers if self._prefetchable(m)), default=0)
+        if numel and (self.bufs is None or self.bufs[0].numel() < numel or self.bufs[0].device != device):
+            self.bufs = [torch.empty(numel, dtype=torch.float16, device=device) for _ in range(self.kBuffers)]
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(device).synchronize()   # one-time: nothing in flight reads that memory
+
+    def take(self, i: int):
+        """The scratch holding layer i's unpacked weight if it was prefetched (and is still current)."""
+        r, self.ready = self.ready, None
+        if r is not None and r[0] == i and r[2] == self._version(self.layers[i]):
+            return r[1]
+        return None
+
+    def after(self, i: int, rows: int) -> None:
+        """Layer i's GEMM has just been enqueued: unpack layer i + 1 next to it."""
+        nxt = i + 1
+        if (nxt >= len(self.layers) or self.bufs is None or rows < ops.PREFETCH_MIN_M
+                or not _lib.OPTIONS["prefetch"] or _lib.OPTIONS["gemm"] == "fused"):
+            return
+        m = self.layers[nxt]
+        if not self._prefetchable(m) or m.qweight.device != self.bufs[0].device \
+                or m.infeatures * m.outfeatures > self.bufs[0].numel():
+            return
+        buf = self.bufs[self.slot]
+        self.slot = (self.slot + 1) % self.kBuffers
+        ops.qlinear_prefetch(m.qweight, m.qzeros, m.scales, m.bits, m.groupsize, buf)
+        self.ready = (nxt, buf, self._version(m))
+
+
+_PREFETCH = weakref.WeakKeyDictionary()   # QuantLinear -> (WeightPrefetchChain, index)
 
 
 class QuantLinear(nn.Module):
@@ -169,8 +247,13 @@ class QuantLinear(nn.Module):
         if sp is not None:      # act-order, short M: gather x's columns, contiguous groups, fused kernel
             return ops.qlinear(ops.gather_cols(x, sp[0]), sp[1], self.qzeros, self.scales, self.bits,
                                self.groupsize, self.bias, None, epilogue, residual)
-        return ops.qlinear(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
-                           self.bias, self.g_idx, epilogue, residual)
+        pf = _PREFETCH.get(self) if x.is_cuda else None
+        wt = pf[0].take(pf[1]) if pf else None
+        y = ops.qlinear(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
+                        self.bias, self.g_idx, epilogue, residual, wt_ready=wt)
+        if pf:
+            pf[0].after(pf[1], x.numel() // max(1, x.shape[-1]))
+        return y
 
     def forward_unpartition(self, x: torch.Tensor, shortcut: torch.Tensor, window_size: int) -> torch.Tensor:
         """``shortcut + window_unpartition(self(x))`` in one kernel (x: windowed tokens)."""
@@ -178,8 +261,13 @@ class QuantLinear(nn.Module):
         if sp is not None:
             return ops.qlinear_unpartition(ops.gather_cols(x, sp[0]), sp[1], self.qzeros, self.scales, self.bits,
                                            self.groupsize, self.bias, shortcut, window_size, None)
-        return ops.qlinear_unpartition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
-                                       self.bias, shortcut, window_size, self.g_idx)
+        pf = _PREFETCH.get(self) if x.is_cuda else None
+        wt = pf[0].take(pf[1]) if pf else None
+        y = ops.qlinear_unpartition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
+                                    self.bias, shortcut, window_size, self.g_idx, wt_ready=wt)
+        if pf:
+            pf[0].after(pf[1], x.numel() // max(1, x.shape[-1]))
+        return y
 
     def forward_partition(self, x: torch.Tensor, window_size: int) -> torch.Tensor:
         """``self(window_partition(x))`` in one kernel: ``x[B, H, W, K]`` in image order ->
@@ -188,8 +276,13 @@ class QuantLinear(nn.Module):
         if sp is not None:
             return ops.qlinear_partition(ops.gather_cols(x, sp[0]), sp[1], self.qzeros, self.scales, self.bits,
                                          self.groupsize, self.bias, window_size, None)
-        return ops.qlinear_partition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
-                                     self.bias, window_size, self.g_idx)
+        pf = _PREFETCH.get(self) if x.is_cuda else None
+        wt = pf[0].take(pf[1]) if pf else None
+        y = ops.qlinear_partition(x, self.qweight, self.qzeros, self.scales, self.bits, self.groupsize,
+                                  self.bias, window_size, self.g_idx, wt_ready=wt)
+        if pf:
+            pf[0].after(pf[1], x.numel() // max(1, x.shape[-1]))
+        return y
 
     def dequantize(self, transposed: bool = False) -> torch.Tensor:
         """fp16 ``W[K, N]`` (``[N, K]`` if transposed) via ``samq_unpack_dequant``."""

@@ -38,13 +38,20 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_strings():
     lib = _lib.load()
-    assert lib.samq_abi_version() == 3
+    assert lib.samq_abi_version() == 4
     assert lib.samq_has_ablations() == 0     # the shipped library holds the product kernels only
     # validation happens before any CUDA call, so these run on a GPU-less box
     rc = lib.samq_unpack_dequant(1, 1, 1, None, 1, 64, 64, 5, 64, 0, None)
     assert rc == _lib.SAMQ_ERR_UNSUPPORTED_BITS and "bits" in _lib.last_error()
     rc = lib.samq_qlinear_fwd(16, 16, 16, 16, None, None, None, 16, None, 4, 100, 128, 4, 128, 0, None)
     assert rc == _lib.SAMQ_ERR_BAD_SHAPE and "K=100" in _lib.last_error()
+    # weight prefetch: int4 only; and a GEMM call without packed pointers needs the prefetched scratch
+    rc = lib.samq_qlinear_prefetch(16, 16, 16, 16, 128, 128, 3, 128, None)
+    assert rc == _lib.SAMQ_ERR_UNSUPPORTED_BITS
+    rc = lib.samq_qlinear_prefetch(16, 16, 16, 16, 100, 128, 4, 128, None)
+    assert rc == _lib.SAMQ_ERR_BAD_SHAPE and "K=100" in _lib.last_error()
+    rc = lib.samq_qlinear_fwd(16, None, None, None, None, None, None, 16, None, 4, 128, 128, 4, 128, 0, None)
+    assert rc == _lib.SAMQ_ERR_BAD_ARG and "prefetched" in _lib.last_error()
     rc = lib.samq_attn_relpos_fwd(16, 16, 16, 16, 1, 32, 32, 4, 80, 0.1, 0, None)
     assert rc == _lib.SAMQ_ERR_BAD_SHAPE
     rc = lib.samq_layernorm_fwd(None, None, None, None, 4, 64, 1e-6, None)

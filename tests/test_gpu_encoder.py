@@ -113,6 +113,55 @@ def test_pad_skipping_block_is_bit_identical(cuda_device, tmp_path, samq_env, ba
     assert torch.equal(old, new)
 
 
+@pytest.mark.parametrize("batch", [1, 3])
+def test_weight_prefetch_is_bit_identical_and_used(cuda_device, tmp_path, samq_env, batch, monkeypatch):
+    """Default: right behind each linear's GEMM the NEXT linear's weight is unpacked next to it
+    (samq_qlinear_prefetch, rotating scratch buffers) and that linear then runs only its GEMM;
+    SAMQ_PREFETCH=0: every linear unpacks its own weight right before its GEMM.  Same kernels'
+    arithmetic -> identical bits; repeated passes (buffer rotation) stay identical; and the
+    prefetch really happens: 4 linears x depth - 1 times per pass."""
+    from sam_quantization_b200 import ops
+    cfg = dict(embed_dim=640, depth=3, num_heads=8, global_attn_indexes=(1,))
+    enc, _ = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=18, device=cuda_device)
+    x = torch.from_numpy(synth.tokens_input(batch, 64, 640, seed=19)).half().to(cuda_device)
+    monkeypatch.setattr(ops, "PREFETCH_MIN_M", 2048)     # the product threshold is batch >= 8
+    calls = []
+    real = ops.qlinear_prefetch
+    monkeypatch.setattr(ops, "qlinear_prefetch", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    with torch.no_grad():
+        samq_env.set("SAMQ_PREFETCH", "0")
+        plain = enc.forward_tokens(x)
+        assert not calls
+        samq_env.set("SAMQ_PREFETCH", "1")
+        outs = [enc.forward_tokens(x) for _ in range(3)]
+    assert len(calls) == 3 * (4 * 3 - 1)
+    for o in outs:
+        assert torch.equal(o, plain)
+
+
+def test_stale_prefetched_weight_is_discarded(cuda_device, tmp_path, monkeypatch):
+    """A prefetched weight is only used if the layer's packed buffers are still the ones that were
+    unpacked: a standalone call leaves the next layer's weight prefetched; re-packing that layer
+    in between must win."""
+    from sam_quantization_b200 import ops, quant_linear as ql
+    monkeypatch.setattr(ops, "PREFETCH_MIN_M", 2048)
+    cfg = dict(embed_dim=640, depth=2, num_heads=8, global_attn_indexes=(1,))
+    enc, _ = build_from_checkpoint(tmp_path, cfg, 4, 128, seed=28, device=cuda_device)
+    x = torch.from_numpy(synth.tokens_input(1, 64, 640, seed=29)).half().to(cuda_device)
+    with torch.no_grad():
+        enc.forward_tokens(x)                               # links the chain
+        lin1, lin2 = enc.blocks[0].mlp.lin1, enc.blocks[0].mlp.lin2
+        h = lin1(x.view(-1, 640))                           # prefetches lin2's weight
+        chain, idx = ql._PREFETCH[lin2]
+        assert chain.ready is not None and chain.ready[0] == idx
+        before = lin2(h)                                    # consumes it
+        lin1(x.view(-1, 640))                               # prefetches lin2 again ...
+        lin2.scales.mul_(2.0)                               # ... then the layer changes
+        after = lin2(h)
+        bias = lin2.bias.float()
+    assert torch.allclose((after.float() - bias), 2.0 * (before.float() - bias), rtol=2e-3, atol=2e-3)
+
+
 def test_vit_l_width_blocks_batched(cuda_device, tmp_path):
     """BASELINE config 2 shapes (ViT-L: dim 1024, 16 heads of 64, batch > 1 so that the GEMMs take
     the unpack-once + CTA-pair path and the windowed block its pad-skipping form), two blocks
@@ -126,6 +175,32 @@ def test_vit_l_width_blocks_batched(cuda_device, tmp_path):
     err, mag, cos = report(y, ref)
     print(f"ViT-L width, batch 3: max-abs {err:.3e} (max|ref| {mag:.3f}) cosine {cos:.7f}")
     assert err <= 1.5e-2 * mag and cos >= 0.9999
+
+
+def test_graphed_encoder_with_weight_prefetch(cuda_device, monkeypatch, samq_env):
+    """The prefetch kernels are captured into the CUDA graph (programmatic edges behind the GEMMs):
+    replays -- several, the scratch buffers rotate -- equal the eager pass without prefetch bit for bit."""
+    from sam_quantization_b200 import ops
+    from sam_quantization_b200.launcher import GraphedEncoder
+    from sam_quantization_b200.synthetic import random_quantized_encoder
+
+    monkeypatch.setattr(ops, "PREFETCH_MIN_M", 2048)
+    enc = random_quantized_encoder("vit_b", 4, 128, seed=5, device=cuda_device, embed_dim=256, depth=3,
+                                   num_heads=4, global_attn_indexes=(1,))
+    g = torch.Generator().manual_seed(10)
+    xs = [torch.randn(2, 3, 1024, 1024, generator=g).half().to(cuda_device) for _ in range(3)]
+    with torch.no_grad():
+        samq_env.set("SAMQ_PREFETCH", "0")
+        plain = [enc(x).clone() for x in xs]
+        samq_env.set("SAMQ_PREFETCH", "1")
+        launches = []
+        real = ops.qlinear_prefetch
+        monkeypatch.setattr(ops, "qlinear_prefetch", lambda *a, **k: (launches.append(1), real(*a, **k))[1])
+        ge = GraphedEncoder(enc, xs[0])
+    assert launches, "the captured pass did not prefetch"
+    for _ in range(2):
+        for x, ref in zip(xs, plain):
+            assert torch.equal(ge(x), ref)
 
 
 def test_graphed_encoder_replay_and_pipelined_host_calls(cuda_device):
