@@ -514,15 +514,9 @@ namespace {
 // windows wh = nH - 1) -- so that all warps do the same amount of work (the earlier version gave a
 // warp 32 consecutive windowed tokens and let it copy whichever of them were padding: most warps
 // had none, a few had 32; 57 us per call for 197 MB of stores).
-__global__ void __launch_bounds__(256)
-fill_pad_rows_kernel(__half* __restrict__ y, const __half* __restrict__ bias, int B, int N, RowMap rm) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int rH = rm.H - (rm.nH - 1) * rm.ws, rW = rm.W - (rm.nW - 1) * rm.ws;   // valid rows / columns of the last windows
-  const int padH = rm.ws - rH, padW = rm.ws - rW;
-  const int colA = rm.H * padW, colB = padH * rm.nW * rm.ws;
-  const int per_image = colA + colB;
-  if (wid >= static_cast<int64_t>(B) * per_image) return;
+__device__ __forceinline__ void fill_pad_row(__half* __restrict__ y, const __half* __restrict__ bias, int N,
+                                             const RowMap& rm, int64_t wid, int per_image, int colA, int rH, int rW,
+                                             int padW, int lane) {
   const int b = static_cast<int>(wid / per_image);
   int p = static_cast<int>(wid - static_cast<int64_t>(b) * per_image);
   int wh, ww, i, j;
@@ -541,6 +535,27 @@ fill_pad_rows_kernel(__half* __restrict__ y, const __half* __restrict__ bias, in
   for (int c = lane; c < N / 8; c += 32) dst[c] = bias ? src[c] : make_uint4(0, 0, 0, 0);
 }
 
+// Launched programmatically BEHIND the qkv GEMM, one block per SM (no shared memory, a few registers:
+// it fits beside the GEMM's persistent CTA): the pad rows are disjoint from the rows the GEMM stores, so
+// the 197 MB of stores (batch 32) run next to the GEMM instead of as a 34-63 us kernel of their own.
+// The output buffer is free for early writes: the GEMM's CTAs have started, i.e. every kernel before it
+// -- every possible reader of the memory the buffer re-uses -- has finished.  The final wait keeps
+// "this grid is complete" implying "the GEMM is complete" for the kernel launched behind it.
+__global__ void __launch_bounds__(256)
+fill_pad_rows_kernel(__half* __restrict__ y, const __half* __restrict__ bias, int B, int N, RowMap rm) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int rH = rm.H - (rm.nH - 1) * rm.ws, rW = rm.W - (rm.nW - 1) * rm.ws;   // valid rows / columns of the last windows
+  const int padH = rm.ws - rH, padW = rm.ws - rW;
+  const int colA = rm.H * padW, colB = padH * rm.nW * rm.ws;
+  const int per_image = colA + colB;
+  const int64_t total = static_cast<int64_t>(B) * per_image;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); wid < total; wid += stride)
+    fill_pad_row(y, bias, N, rm, wid, per_image, colA, rH, rW, padW, lane);
+  pdl_wait();
+}
+
 }  // namespace
 }  // namespace samq
 
@@ -557,17 +572,20 @@ extern "C" int samq_qlinear_partition_fwd(const void* x, const int32_t* qweight,
   const RowMap to_win = {ws, H, W, nH, nW, 1};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SAMQ_REQUIRE(y != nullptr, SAMQ_ERR_BAD_ARG, "samq_qlinear_partition_fwd: null output");
-  // pad rows first (they are disjoint from the rows the GEMM stores): the GEMM is then the LAST kernel
-  // of this call, and a weight prefetch launched behind it runs next to it
+  int rc = qlinear_impl("samq_qlinear_partition_fwd", x, qweight, qzeros, scales, g_idx, bias, nullptr, y, workspace,
+                        M_img, K, N, bits, groupsize, SAMQ_EPI_NONE, to_win, st);
+  if (rc != SAMQ_OK) return rc;
+  // pad rows (disjoint from the rows the GEMM stores): launched behind the GEMM, runs next to it
   if (nH * ws != H || nW * ws != W) {
     const int64_t pad_rows = static_cast<int64_t>(B) * (H * (nW * ws - W) + (nH * ws - H) * nW * ws);
-    fill_pad_rows_kernel<<<static_cast<unsigned>((pad_rows + 7) / 8), 256, 0, st>>>(
-        reinterpret_cast<__half*>(y), reinterpret_cast<const __half*>(bias), B, N, to_win);
+    const int64_t blocks = (pad_rows + 7) / 8;
+    const int grid = static_cast<int>(blocks < num_sms() ? blocks : num_sms());
+    launch_pdl(1, fill_pad_rows_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<__half*>(y),
+               reinterpret_cast<const __half*>(bias), B, N, to_win);
     count_launch();
-    if (int rc = check_launch("fill_pad_rows_kernel"); rc != SAMQ_OK) return rc;
+    return check_launch("fill_pad_rows_kernel");
   }
-  return qlinear_impl("samq_qlinear_partition_fwd", x, qweight, qzeros, scales, g_idx, bias, nullptr, y, workspace,
-                      M_img, K, N, bits, groupsize, SAMQ_EPI_NONE, to_win, st);
+  return SAMQ_OK;
 }
 
 extern "C" int samq_qlinear_prefetch(const int32_t* qweight, const int32_t* qzeros, const void* scales,
