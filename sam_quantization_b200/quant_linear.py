@@ -94,6 +94,10 @@ def unpack_fields(words: torch.Tensor, bits: int) -> torch.Tensor:
     raise NotImplementedError("Only 2,3,4,8 bits are supported.")
 
 
+def _no_chain():
+    return None
+
+
 class WeightPrefetchChain:
     """Weight prefetch over a fixed execution order of int4 ``QuantLinear`` layers (the four linears of
     every encoder block).  For long M a layer runs as "unpack the weight once into an fp16 scratch, then
@@ -125,6 +129,9 @@ class WeightPrefetchChain:
 
     def __deepcopy__(self, memo):   # a copied encoder links its own chain on first use
         return None
+
+    def __reduce__(self):           # ... and so does an unpickled one (no scratch buffers in the pickle)
+        return (_no_chain, ())
 
     @staticmethod
     def _version(m):

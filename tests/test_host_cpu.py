@@ -255,3 +255,21 @@ def test_get_rel_pos_matches_reference_including_interpolation(golden_dir):
     # SAM's own case stays the plain gather
     t = torch.arange(27, dtype=torch.float32)[:, None].repeat(1, 2)
     assert torch.equal(ie.get_rel_pos(14, 14, t)[3, 5], t[3 - 5 + 13])
+
+
+def test_prefetch_chain_state_does_not_travel_with_the_model():
+    """The weight-prefetch chain (runtime state: layer order + scratch buffers) is dropped by
+    deepcopy and pickle -- the copy links its own on first use -- and never enters state_dict."""
+    import copy
+    import pickle
+
+    from sam_quantization_b200.quant_linear import QuantLinear, WeightPrefetchChain, _PREFETCH
+
+    layers = [QuantLinear(4, 128, 128, 256, True), QuantLinear(4, 128, 256, 128, True)]
+    holder = torch.nn.Sequential(*layers)
+    holder.__dict__["_pf_chain"] = chain = WeightPrefetchChain(layers)
+    assert _PREFETCH[layers[1]] == (chain, 1)
+    assert copy.deepcopy(holder).__dict__["_pf_chain"] is None
+    assert pickle.loads(pickle.dumps(holder)).__dict__["_pf_chain"] is None
+    assert not any("pf" in k for k in holder.state_dict())
+    assert chain.take(0) is None            # nothing prefetched: the layer unpacks its own weight
