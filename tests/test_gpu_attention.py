@@ -37,6 +37,44 @@ def test_attention_test_op_shapes(cuda_device, B, E, heads, hd, relw):
     assert err <= ATOL and cos >= 0.9999, (err, mag, cos)
 
 
+@pytest.mark.parametrize("B,E", [(800, 14), (32, 64)])
+def test_full_size_properties_at_the_benchmarked_batch(cuda_device, B, E):
+    """BASELINE's full sizes (batch 32 of ViT-H: 800 windows x 16 heads x 196 keys, 32 images x 16 heads
+    x 4096 keys), where the oracle would take minutes: size-independent properties of softmax(.) V.
+    (1) With V = 1 every output is a convex combination of ones: exactly 1 up to the fp16 roundings of P
+    and of O / l.  (2) The output is linear in V: attn(V1 + V2) = attn(V1) + attn(V2) for the same
+    scores.  (3) No op crosses the batch: the first and last items recomputed alone give the same bits.
+    (4) A sample of items against the oracle."""
+    heads, hd = 16, 80
+    D = heads * hd
+    g = torch.Generator(device=cuda_device).manual_seed(31)
+    qkv = torch.empty(B, E * E, 3 * D, device=cuda_device, dtype=torch.float16).normal_(0.0, 0.5, generator=g)
+    rph = torch.empty(2 * E - 1, hd, device=cuda_device, dtype=torch.float16).normal_(0.0, 0.3, generator=g)
+    rpw = torch.empty(2 * E - 1, hd, device=cuda_device, dtype=torch.float16).normal_(0.0, 0.3, generator=g)
+    scale = hd ** -0.5
+    run = lambda t, b=B: ops.attn_relpos(t, rph, rpw, b, E, E, heads, scale)
+    out = run(qkv)
+    assert not torch.isnan(out).any()
+    ones = qkv.clone()
+    ones[..., 2 * D:] = 1.0
+    o1 = run(ones)
+    assert float((o1.float() - 1.0).abs().max()) <= 2e-3
+    v2 = torch.empty(B, E * E, D, device=cuda_device, dtype=torch.float16).normal_(0.0, 0.5, generator=g)
+    other = qkv.clone()
+    other[..., 2 * D:] = v2
+    both = qkv.clone()
+    both[..., 2 * D:] = (qkv[..., 2 * D:].float() + v2.float()).half()
+    lin = (run(both).float() - out.float() - run(other).float()).abs().max()
+    assert float(lin) <= 4e-3, float(lin)     # three fp16-rounded outputs + the rounding of V1 + V2
+    k = 3 if E == 14 else 1
+    assert torch.equal(out[:k], run(qkv[:k].contiguous(), k)) and torch.equal(out[-k:], run(qkv[-k:].contiguous(), k))
+    pick = [0, B // 2, B - 1][:k if E == 64 else 3]
+    ref = oe.attention_core(qkv[pick].cpu(), rph.cpu(), rpw.cpu(), len(pick), E, E, heads, scale, "reference",
+                            round_tables=True)
+    err, mag, cos = report(out[pick], ref)
+    assert err <= ATOL and cos >= 0.9999, (err, mag, cos)
+
+
 @pytest.mark.parametrize("B,heads,hd", [(1, 1, 80), (1, 3, 64), (10, 16, 80), (37, 5, 64), (60, 16, 80)])
 def test_windowed_item_scheduling(cuda_device, B, heads, hd):
     """The windowed kernel is persistent (one CTA per SM looping over (window, head) items):
