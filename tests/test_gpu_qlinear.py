@@ -108,6 +108,40 @@ def test_full_size_m32768_against_fp32_gemm_of_exact_weights(cuda_device, samq_e
     assert (y2.float() - 2 * y.float()).abs().max().item() <= 2.0 ** -23
 
 
+@pytest.mark.parametrize("K,N,epilogue,residual", [(1280, 3840, "none", False), (1280, 1280, "none", True),
+                                                   (1280, 5120, "gelu", False), (5120, 1280, "none", True)])
+def test_the_four_vith_linears_at_the_benchmarked_batch(cuda_device, K, N, epilogue, residual):
+    """The bench's own GEMMs: M = 131072 rows (batch 32), each ViT-H layer shape with its epilogue.
+    (1) 2048-row slices (first, a middle one, last) recomputed alone -- same kernel path -- give the
+    same bits: no tile depends on another.  (2) The same slices against an fp32 GEMM of the bit-exact
+    dequantised weight with the epilogue applied in fp32 (one fp16 ulp of the output's magnitude;
+    GELU is the exact erf form)."""
+    M = 131072
+    qw, qz, sc, _ = rand_packed(K, N, 4, 128, seed=14)
+    tq, tz, ts = dev(qw, cuda_device), dev(qz, cuda_device), dev(sc, cuda_device)
+    g = torch.Generator(cuda_device).manual_seed(3)
+    x = torch.randn(M, K, device=cuda_device, generator=g).half()
+    b = torch.randn(N, device=cuda_device, generator=g).half()
+    r = torch.randn(M, N, device=cuda_device, generator=g).half() if residual else None
+    epi = _lib.EPI_GELU if epilogue == "gelu" else _lib.EPI_NONE
+    y = ops.qlinear(x, tq, tz, ts, 4, 128, b, epilogue=epi, residual=r)
+    w = ops.unpack_dequant(tq, tz, ts, 4, 128).float()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for lo in (0, 61440 + 256, M - 2048):
+        sl = slice(lo, lo + 2048)
+        alone = ops.qlinear(x[sl].contiguous(), tq, tz, ts, 4, 128, b, epilogue=epi,
+                            residual=None if r is None else r[sl].contiguous())
+        assert torch.equal(y[sl], alone), lo
+        ref = x[sl].float() @ w + b.float()
+        if epilogue == "gelu":
+            ref = torch.nn.functional.gelu(ref)
+        if r is not None:
+            ref = ref + r[sl].float()
+        err = (y[sl].float() - ref).abs().max().item()
+        mag = ref.abs().max().item()
+        assert err <= ULP * mag + 1e-6, (lo, err, mag)
+
+
 def test_module_forward_and_reference_entry_point(cuda_device):
     """QuantLinear.forward and triton_matmul4 (the reference's public entry, quant_linear.py:355)."""
     K, N, gs = 1280, 1280, 128
