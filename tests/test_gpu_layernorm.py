@@ -24,6 +24,23 @@ def test_layernorm(cuda_device, C):
     assert err <= 2.0 ** -10 * mag and cos > 0.999999     # one fp16 ulp at the output magnitude
 
 
+def test_layernorm_at_the_benchmarked_batch(cuda_device):
+    """131072 x 1280 rows (batch 32 of ViT-H; ragged tail: + 5 rows), with a large common offset in
+    the input (mean >> std: the two-pass statistics must not cancel): every row against an fp32
+    LayerNorm on the GPU, and slice independence (first / last rows recomputed alone, same bits)."""
+    rows, C = 131072 + 5, 1280
+    g = torch.Generator(cuda_device).manual_seed(4)
+    x = (torch.randn(rows, C, device=cuda_device, generator=g) * 1.5 + 40.0).half()
+    w = (1 + 0.1 * torch.randn(C, device=cuda_device, generator=g)).half()
+    b = (0.1 * torch.randn(C, device=cuda_device, generator=g)).half()
+    y = ops.layernorm(x, w, b, 1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w.float(), b.float(), 1e-6)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2.0 ** -10 * ref.abs().max().item() + 1e-6, err      # one fp16 ulp of the output magnitude
+    for sl in (slice(0, 37), slice(rows - 37, rows)):
+        assert torch.equal(y[sl], ops.layernorm(x[sl].contiguous(), w, b, 1e-6))
+
+
 @pytest.mark.parametrize("B,H,W,C", [(1, 64, 64, 1280), (2, 64, 64, 768), (3, 20, 30, 64)])
 def test_layernorm_partition(cuda_device, B, H, W, C):
     g = torch.Generator().manual_seed(1)
